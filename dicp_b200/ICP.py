@@ -1,0 +1,232 @@
+"""`ICP` — host-side mirror of the reference's public class (`dICP/ICP.py:14-511`).
+
+Same constructor, same `icp` / `dICP` / `batch_size_handling` signatures, same YAML keys,
+same result dictionary.  What differs is where the work happens: after the (host-side,
+once-per-call) batch normalisation, the whole Gauss-Newton loop of `ICP.py:125-303` —
+transform, nearest neighbour, residual, trim / robust weights, Jacobian, normal equations,
+solve, exp-map update, convergence bookkeeping — runs as hand-written sm_100a kernels
+behind one `torch.autograd.Function` (`_functions.ICPFunction`), and so does its reverse
+pass.  No CPU fallback: without a CUDA device `icp()` raises.
+"""
+import os.path as osp
+
+import torch
+import yaml
+
+from . import _functions
+from .nn import nn
+
+
+def _is_empty(x):
+    return x is None or len(x) == 0
+
+
+class ICP:
+    def __init__(self, config_path=None, icp_type='pt2pl', max_iterations=100, tolerance=1e-12, differentiable=True):
+        if config_path is None:
+            # same default location as the reference: <package>/../config/dICP_config.yaml (ICP.py:17-19)
+            config_path = osp.join(osp.dirname(osp.abspath(__file__)), '..', 'config', 'dICP_config.yaml')
+        with open(config_path, 'r') as f:
+            self.config = yaml.safe_load(f)
+
+        params = self.config['dICP']['parameters']
+        logging = self.config['dICP']['logging']
+        func = self.config['dICP']['functionality']
+        self.icp_type = icp_type
+        self.max_iterations = max_iterations
+        self.tolerance = tolerance
+        self.const_iter = params['const_iter']
+        self.verbose = logging['verbose']
+        self.target_pad_val = params['target_pad_val']
+        self.source_zeroes_are_pad = params['source_zeroes_are_pad']
+        self.match_ratio_thresh = logging['matched_ratio_thresh']
+        self.diff = differentiable
+        self.nn = nn(self.diff, use_gumbel=func['gumbel'], eps=func['gumbel_eps'], tau=func['gumbel_tau'])
+        # not in the reference: how often the host polls the device-side "all converged" flag
+        # when const_iter is False (the reference synchronises every iteration, ICP.py:240)
+        self.check_every = 1
+        # not in the reference: CUDA device used when the inputs live on the CPU
+        self.device = None
+
+    def icp(self, source, target, T_init, weight=None, trim_dist=None, loss_fn=None, dim=3):
+        return self.dICP(source, target, T_init, weight, trim_dist, loss_fn, dim)
+
+    # ---------------------------------------------------------------------------------
+    def dICP(self, source, target, T_init, weight=None, trim_dist=None, loss_fn=None, dim=3):
+        """Point-to-point / point-to-plane ICP; argument and return conventions are those of
+        the reference docstring (ICP.py:50-78): returns a dict with 'pc' (N,n,3), 'T' (N,4,4),
+        'costs' (N,K,1), 'deltas' (N,K,6,1), 'weights' (N,K,n|3n,1) and 'stats'
+        {'converged','iterations','matched_ratio'} (each (N,))."""
+        assert dim == 2 or dim == 3, "dim must be 2 or 3"
+        source, target, T_init, w_init = self.batch_size_handling(source, target, T_init, weight)
+        assert source.dtype == target.dtype == T_init.dtype
+        N, n = source.shape[0], source.shape[1]
+        pt2pl = self.icp_type == 'pt2pl'
+        if pt2pl:
+            assert target.shape[2] == 6          # normals are required (ICP.py:103)
+        else:
+            target = target[:, :, :3]
+        if self.diff and self.nn.use_gumbel:
+            raise NotImplementedError("the Gumbel-softmax neighbour search (config functionality.gumbel) is "
+                                      "outside the scope of the CUDA solver loop")
+
+        if dim == 2:
+            # planar problem: drop z of the points and of the normals (ICP.py:107-116)
+            zs = source.new_zeros((N, n, 1))
+            source = torch.cat((source[:, :, :2], zs), dim=2)
+            zt = target.new_zeros((N, target.shape[1], 1))
+            if pt2pl:
+                target = torch.cat((target[:, :, :2], zt, target[:, :, 3:5], zt), dim=2)
+            else:
+                target = torch.cat((target[:, :, :2], zt), dim=2)
+
+        # per-point prior weights; pt2pt carries them x3-repeated (ICP.py:508-509)
+        w_point = w_init if pt2pl else w_init[:, ::3]
+
+        out_dev = source.device
+        dev = self._compute_device(out_dev)
+        loss_name = loss_fn['name'] if loss_fn is not None else None
+        loss_metric = loss_fn['metric'] if loss_fn is not None else 1.0
+        params = _functions.make_params(
+            self.icp_type, dim, self.diff, loss_name, loss_metric, trim_dist,
+            self.config['dICP']['parameters']['tanh_steepness'], self.tolerance, self.max_iterations,
+            self.const_iter, self.match_ratio_thresh, self.check_every)
+
+        pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
+            source.to(dev), target.to(dev), T_init.to(dev), w_point.to(dev), params)
+
+        if self.verbose:
+            print("ICP converged in {} iterations".format(deltas.shape[1]))
+            print("Final del_T_ts: {}".format(torch.linalg.norm(deltas[:, -1])))
+
+        back = (lambda t: t) if out_dev == dev else (lambda t: t.to(out_dev))
+        return {
+            "pc": back(pc),
+            "T": back(T),
+            "costs": back(costs).unsqueeze(-1),
+            "deltas": back(deltas).unsqueeze(-1),
+            "weights": back(weights).unsqueeze(-1),
+            "stats": {"converged": back(converged), "iterations": back(num_iters), "matched_ratio": back(match_ratio)},
+        }
+
+    def _compute_device(self, input_device):
+        _functions.require_cuda()
+        if input_device.type == 'cuda':
+            return input_device
+        return torch.device(self.device) if self.device is not None else torch.device('cuda', torch.cuda.current_device())
+
+    # ---------------------------------------------------------------------------------
+    def batch_size_handling(self, source, target, T_init=None, weight=None):
+        """Normalise every accepted input form to dense batch tensors (ICP.py:305-511):
+        source (n,3|6) | (N,n,3|6) | list of (n_i,3|6)  -> (N,n,3), zero-padded, zero weight on pads
+        target (m,3|6) | (N,m,3|6) | list of (m_i,3|6)  -> (N,m,S), padded with max(source)*target_pad_val
+        T_init (4,4) | (N,4,4) | list                   -> (N,4,4) or None
+        weight None | (n,) | (N,n) | list (entries may be None) -> w (N,n), or (N,3n) for pt2pt.
+        Empty / missing clouds become a single phony point with zero weight."""
+        rows_per_point = 3 if self.icp_type == 'pt2pt' else 1
+        if weight is not None:
+            if isinstance(source, list):
+                assert len(source) == len(weight), "weight must be list of same length as source"
+            else:
+                assert source.shape[0] == weight.shape[0], "weight must have same number of rows as source"
+
+        if _is_empty(source) or _is_empty(target):
+            # whole source or target missing: phony CPU/fp32 problem that returns T = I (ICP.py:329-346)
+            w = torch.zeros((1, rows_per_point), dtype=torch.float32)
+            return (torch.zeros((1, 1, 3), dtype=torch.float32), torch.zeros((1, 1, 6), dtype=torch.float32),
+                    torch.eye(4, dtype=torch.float32).unsqueeze(0), w)
+
+        # dtype / device / column count come from the first non-empty target (ICP.py:347-358)
+        dev, dt, tcols = "cpu", torch.float32, None
+        for t_i in target:
+            if t_i is not None and len(t_i) > 0:
+                dev, dt = t_i.device, t_i.dtype
+                tcols = t_i.shape[0] if (not isinstance(target, list) and target.dim() == 2) else t_i.shape[1]
+                break
+
+        # ---- source and prior weights ------------------------------------------------
+        if isinstance(source, list):
+            clouds, priors = [], []
+            for i, s_i in enumerate(source):
+                empty = len(s_i) == 0
+                if empty:
+                    s_i = torch.zeros((1, 3), dtype=dt, device=dev)
+                if i > 0 and (s_i.dim() != 2 or s_i.shape[1] not in (3, 6)):
+                    raise ValueError("source list must contain (n x 3/6) tensors")
+                prior = torch.ones(s_i.shape[0], dtype=dt, device=dev)
+                if weight is not None and weight[i] is not None and not (empty and i == 0):
+                    assert len(weight[i]) == s_i.shape[0], "weight must have same number of rows as source"
+                    prior = weight[i] * prior
+                if empty:
+                    prior = 0.0 * prior
+                clouds.append(s_i[:, :3])
+                priors.append(prior)
+            n_max = max(c.shape[0] for c in clouds)
+            source_batch = torch.stack([self._pad_rows(c, n_max, 0.0) for c in clouds], dim=0)
+            w = torch.stack([self._pad_rows(p_.unsqueeze(-1), n_max, 0.0).squeeze(-1) for p_ in priors], dim=0)
+        elif source.dim() == 2 and source.shape[1] in (3, 6):
+            source_batch = source[:, :3].unsqueeze(0)
+            w = torch.ones((1, source_batch.shape[1]), dtype=dt, device=dev) if weight is None else weight.unsqueeze(0)
+        elif source.dim() == 3 and source.shape[2] in (3, 6):
+            source_batch = source[:, :, :3]
+            w = torch.ones(source_batch.shape[:2], dtype=dt, device=dev) if weight is None else weight
+        else:
+            raise ValueError("source must be (n x 3/6) or (N x n x 3/6) or list len(N) (n_N x 3/6)")
+
+        if self.source_zeroes_are_pad:
+            w = w * (torch.linalg.norm(source_batch, dim=2) != 0.0).to(dt)
+
+        # ---- target ------------------------------------------------------------------
+        if isinstance(target, list):
+            pad_value = torch.max(source_batch) * self.target_pad_val       # ICP.py:460
+            clouds, dead = [], []
+            for i, t_i in enumerate(target):
+                if len(t_i) == 0:
+                    t_i = torch.zeros((1, tcols), dtype=dt, device=dev)
+                    dead.append(i)
+                if i > 0 and (t_i.dim() != 2 or t_i.shape[1] != tcols):
+                    raise ValueError("target list must contain (m x 3/6) tensors. All tensors must have same number of columns")
+                clouds.append(t_i)
+            m_max = max(c.shape[0] for c in clouds)
+            target_batch = torch.stack([self._pad_rows(c, m_max, pad_value) for c in clouds], dim=0)
+            if dead:
+                alive = torch.ones((w.shape[0], 1), dtype=w.dtype, device=w.device)
+                alive[dead] = 0.0
+                w = w * alive                                               # ICP.py:456, 467
+        elif target.dim() == 2 and target.shape[1] in (3, 6):
+            target_batch = target.unsqueeze(0)
+        elif target.dim() == 3 and target.shape[2] in (3, 6):
+            target_batch = target
+        else:
+            raise ValueError("target must be (m x 3/6) or (N x m x 3/6) or list len(N) (m_N x 3/6)")
+
+        # ---- initial transform ---------------------------------------------------------
+        if T_init is None:
+            T_batch = None
+        elif isinstance(T_init, list):
+            T_batch = torch.stack(T_init, dim=0)
+        elif T_init.shape == (4, 4):
+            T_batch = T_init.unsqueeze(0)
+        elif T_init.dim() == 3 and T_init.shape[1:] == (4, 4):
+            T_batch = T_init
+        else:
+            raise ValueError("T_init must be (4 x 4) or (N x 4 x 4) or list len(N) (4 x 4)")
+
+        if rows_per_point == 3:
+            w = w.repeat_interleave(3, dim=1)                               # ICP.py:508-509
+        return source_batch, target_batch, T_batch, w
+
+    @staticmethod
+    def _pad_rows(x, rows, value):
+        """(k,c) -> (rows,c), new rows filled with `value` (a float or a 0-d tensor)."""
+        short = rows - x.shape[0]
+        if short <= 0:
+            return x
+        fill = value * torch.ones((short, x.shape[1]), dtype=x.dtype, device=x.device)
+        return torch.cat((x, fill), dim=0)
+
+    # ---------------------------------------------------------------------------------
+    def pt2pt_dICP_SVD(self, source, target, T_init, trim_dist=None, huber_delta=None, dim=3):
+        """Kabsch / SVD point-to-point ICP (ICP.py:533-591; 'not yet integrated' upstream).
+        SURVEY.md §8(f-2): scheduled after the Gauss-Newton path."""
+        raise NotImplementedError("pt2pt_dICP_SVD: the Kabsch path is not built yet (SURVEY.md §8 f-2)")

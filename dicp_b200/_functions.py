@@ -1,0 +1,163 @@
+"""torch.autograd.Function wrappers around the C ABI (include/dicp_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams and carries the autograd
+graph edge; every number is produced by libdicp_b200.so."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import DicpParams, check, load_library, ptr, require_cuda, stream_ptr, suffix
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def nn_argmin(x, y, return_d2=False):
+    """x (N,n,3), y (N,m,3|6) CUDA tensors -> idx (N,n) int32 [, d2 (N,n)] (nn.py:32-35)."""
+    require_cuda()
+    lib = load_library()
+    assert x.is_cuda and y.is_cuda and x.dtype == y.dtype
+    x = x.detach().contiguous()
+    y = y.detach().contiguous()
+    N, n, _ = x.shape
+    m, S = y.shape[1], y.shape[2]
+    sfx = suffix(x.dtype)
+    idx = torch.empty((N, n), dtype=torch.int32, device=x.device)
+    d2 = torch.empty((N, n), dtype=x.dtype, device=x.device) if return_d2 else None
+    ws = _workspace(lib.dicp_nn_workspace_bytes(N, n, m, x.element_size()), x.device)
+    with torch.cuda.device(x.device):
+        rc = getattr(lib, "dicp_nn_argmin_" + sfx)(ptr(x), ptr(y), N, n, m, S, ptr(idx), ptr(d2), ptr(ws), ws.numel(),
+                                                   stream_ptr(x.device))
+    check(rc, "dicp_nn_argmin_" + sfx)
+    return (idx, d2) if return_d2 else idx
+
+
+class GatherRows(torch.autograd.Function):
+    """neighbours = y[b, idx[b,i], :]; backward is the scatter-add into y (nn.py:37-38)."""
+
+    @staticmethod
+    def forward(ctx, y, idx):
+        lib = load_library()
+        y = y.contiguous()
+        N, m, S = y.shape
+        n = idx.shape[1]
+        out = torch.empty((N, n, S), dtype=y.dtype, device=y.device)
+        sfx = suffix(y.dtype)
+        with torch.cuda.device(y.device):
+            rc = getattr(lib, "dicp_gather_rows_" + sfx)(ptr(y), ptr(idx), N, n, m, S, ptr(out), stream_ptr(y.device))
+        check(rc, "dicp_gather_rows_" + sfx)
+        ctx.save_for_backward(idx)
+        ctx.shape = (N, m, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = load_library()
+        (idx,) = ctx.saved_tensors
+        N, m, S = ctx.shape
+        n = idx.shape[1]
+        g = grad_out.contiguous()
+        gy = torch.zeros((N, m, S), dtype=g.dtype, device=g.device)
+        sfx = suffix(g.dtype)
+        with torch.cuda.device(g.device):
+            rc = getattr(lib, "dicp_gather_rows_bwd_" + sfx)(ptr(g), ptr(idx), N, n, m, S, ptr(gy), stream_ptr(g.device))
+        check(rc, "dicp_gather_rows_bwd_" + sfx)
+        return gy, None
+
+
+def make_params(icp_type, dim, differentiable, loss_name, loss_metric, trim_dist, tanh_steepness, tolerance,
+                max_iterations, const_iter, match_ratio_thresh, check_every=1):
+    if loss_name not in _lib.LOSS_IDS:
+        raise ValueError("Invalid loss name: {}".format(loss_name))          # loss.py:19
+    p = DicpParams()
+    p.icp_type = _lib.DICP_PT2PL if icp_type == "pt2pl" else _lib.DICP_PT2PT
+    p.dim = int(dim)
+    p.differentiable = int(bool(differentiable))
+    p.loss_id = _lib.LOSS_IDS[loss_name]
+    use_trim = trim_dist is not None and trim_dist >= 0.0                    # ICP.py:153
+    p.use_trim = int(use_trim)
+    p.max_iterations = int(max_iterations)
+    p.const_iter = int(bool(const_iter))
+    p.check_every = int(check_every)
+    p.loss_metric = float(loss_metric) if loss_name is not None else 1.0
+    p.trim_dist = float(trim_dist) if use_trim else 0.0
+    p.tanh_steepness = float(tanh_steepness)
+    p.tolerance = float(tolerance)
+    p.match_ratio_thresh = float(match_ratio_thresh)
+    return p
+
+
+class ICPFunction(torch.autograd.Function):
+    """The whole solver loop (ICP.py:125-303) as one autograd node.
+
+    forward(source (N,n,3), target (N,m,S), T_init (N,4,4), w_init (N,n) | None, params)
+      -> pc, T (differentiable) and deltas, weights, costs, converged, num_iters, match_ratio
+         (detached / non-differentiable, ICP.py:220-229, 288-292)."""
+
+    @staticmethod
+    def forward(ctx, source, target, T_init, w_init, params):
+        require_cuda()
+        lib = load_library()
+        dev, dt = source.device, source.dtype
+        assert source.is_cuda and target.device == dev and T_init.device == dev
+        source, target, T_init = source.contiguous(), target.contiguous(), T_init.contiguous()
+        if w_init is not None:
+            w_init = w_init.contiguous()
+        N, n, _ = source.shape
+        m, S = target.shape[1], target.shape[2]
+        K = params.max_iterations
+        R = 1 if params.icp_type == _lib.DICP_PT2PL else 3
+        sfx = suffix(dt)
+        pc = torch.empty((N, n, 3), dtype=dt, device=dev)
+        T = torch.empty((N, 4, 4), dtype=dt, device=dev)
+        deltas = torch.empty((N, K, 6), dtype=dt, device=dev)
+        weights = torch.empty((N, K, n * R), dtype=dt, device=dev)
+        costs = torch.empty((N, K), dtype=dt, device=dev)
+        converged = torch.empty((N,), dtype=torch.uint8, device=dev)
+        num_iters = torch.empty((N,), dtype=dt, device=dev)
+        match_ratio = torch.empty((N,), dtype=dt, device=dev)
+        saved_idx = torch.empty((K, N, n), dtype=torch.int32, device=dev)
+        saved_state = torch.empty((K + 1, N, _lib.STATE_STRIDE), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.dicp_icp_workspace_bytes(N, n, m, source.element_size()), dev)
+        iters = ctypes.c_int32(0)
+        with torch.cuda.device(dev):
+            rc = getattr(lib, "dicp_icp_forward_" + sfx)(
+                ptr(source), ptr(target), ptr(T_init), ptr(w_init), N, n, m, S, ctypes.byref(params),
+                ptr(pc), ptr(T), ptr(deltas), ptr(weights), ptr(costs), ptr(converged), ptr(num_iters), ptr(match_ratio),
+                ptr(saved_idx), ptr(saved_state), ctypes.byref(iters), ptr(ws), ws.numel(), stream_ptr(dev))
+        check(rc, "dicp_icp_forward_" + sfx)
+        k_run = int(iters.value)
+        ctx.params = params
+        ctx.k_run = k_run
+        ctx.dims = (N, n, m, S)
+        ctx.has_w = w_init is not None
+        ctx.save_for_backward(source, target, w_init if w_init is not None else source.new_empty(0),
+                              saved_idx, saved_state)
+        ctx.ws = ws
+        outs = (pc, T, deltas[:, :k_run], weights[:, :k_run], costs[:, :k_run], converged.bool(), num_iters, match_ratio)
+        ctx.mark_non_differentiable(*outs[2:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pc, g_T, *_unused):
+        lib = load_library()
+        source, target, w_init, saved_idx, saved_state = ctx.saved_tensors
+        N, n, m, S = ctx.dims
+        dev, dt = source.device, source.dtype
+        sfx = suffix(dt)
+        g_pc = g_pc.contiguous() if g_pc is not None else None
+        g_T = g_T.contiguous() if g_T is not None else None
+        g_src = torch.empty_like(source)
+        g_tgt = torch.empty_like(target)
+        g_w = torch.empty((N, n), dtype=dt, device=dev) if (ctx.has_w and ctx.needs_input_grad[3]) else None
+        g_T0 = torch.empty((N, 4, 4), dtype=dt, device=dev)
+        ws = ctx.ws
+        with torch.cuda.device(dev):
+            rc = getattr(lib, "dicp_icp_backward_" + sfx)(
+                ptr(source), ptr(target), ptr(w_init) if ctx.has_w else None, N, n, m, S, ctypes.byref(ctx.params), ctx.k_run,
+                ptr(saved_idx), ptr(saved_state), ptr(g_T), ptr(g_pc), ptr(g_src), ptr(g_tgt), ptr(g_w), ptr(g_T0),
+                ptr(ws), ws.numel(), stream_ptr(dev))
+        check(rc, "dicp_icp_backward_" + sfx)
+        return g_src, g_tgt, g_T0, g_w, None

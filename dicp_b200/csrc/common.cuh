@@ -1,0 +1,120 @@
+// common.cuh — internal helpers shared by the .cu files of libdicp_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dicp_b200.h"
+#include "dicp_math.cuh"
+
+namespace dicp {
+
+void set_error(const char* fmt, ...);
+
+#define DICP_CHECK_ARG(cond, msg)                       \
+  do {                                                  \
+    if (!(cond)) {                                      \
+      dicp::set_error("%s: %s", __func__, msg);         \
+      return DICP_ERR_ARG;                              \
+    }                                                   \
+  } while (0)
+
+#define DICP_CUDA(call)                                                            \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      dicp::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return (int)_e;                                                              \
+    }                                                                              \
+  } while (0)
+
+#define DICP_LAUNCH_CHECK()                                                        \
+  do {                                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) {                                                       \
+      dicp::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return (int)_e;                                                              \
+    }                                                                              \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  size_t size, off;
+  Arena(void* p, size_t n) : base((char*)p), size(n), off(0) {}
+  template <typename U> U* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(U));
+    if (base != nullptr && off + bytes > size) { off += bytes; return nullptr; }
+    U* r = base ? (U*)(base + off) : nullptr;
+    off += bytes;
+    return r;
+  }
+};
+
+inline WeightParams make_weight_params(const dicp_params* p) {
+  WeightParams w;
+  w.loss_id = p->loss_id;
+  w.use_trim = p->use_trim;
+  w.diff = p->differentiable;
+  w.c = p->loss_metric;
+  w.tau = p->trim_dist;
+  w.steep = p->tanh_steepness;
+  w.thresh = p->match_ratio_thresh;
+  return w;
+}
+
+// device control block of one forward call
+struct Ctrl {
+  int stop;        // all pairs below tolerance (only raised when !const_iter)
+  int iters_run;   // iterations actually executed
+  int singular;    // a normal matrix was exactly singular
+  int ticket;      // per-iteration arrival counter of the update kernel
+  int nbelow;      // per-iteration count of pairs below tolerance
+};
+
+// ---- nearest neighbour (nn_kernels.cu) ------------------------------------------------
+size_t nn_workspace_bytes(int N, int n, int m, int elem_size);
+// packed targets: [N, m_pad] of (x,y,z,0) in T, m_pad = round_up(m, NN_CHUNK), sentinel rows
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; };
+template <> struct Vec4<double> { typedef double4 type; };
+constexpr int NN_CHUNK = 16;
+inline int nn_m_pad(int m) { return (m + NN_CHUNK - 1) / NN_CHUNK * NN_CHUNK; }
+
+template <typename T>
+int nn_pack_targets(const T* tgt, int N, int m, int S, typename Vec4<T>::type* packed, cudaStream_t st);
+// state: nullptr (queries are used as given) or pointer to this iteration's saved-state
+// records [N, ST_STRIDE] whose C,r transform the queries first (ICP.py:137).
+template <typename T>
+int nn_search(const T* q, const double* state, const typename Vec4<T>::type* packed, int N, int n, int m,
+              int32_t* idx_out, T* d2_out, const int* stop_flag, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t nn_search_ws_bytes(int N, int n, int m, int elem_size);
+
+// ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------
+int gn_blocks_per_pair(int n);
+template <typename T>
+int gn_accumulate(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* state,
+                  int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,
+                  double* partials, const int* stop_flag, cudaStream_t st);
+
+
+// ---- workspace of one forward / backward call (gn_kernels.cu) -------------------------
+constexpr int BW_STRIDE = 32;   // doubles per pair of backward carry: Cbar 9, rbar 3, lambda 6, delta 6, active 1
+constexpr int BW_CBAR = 0, BW_RBAR = 9, BW_LAM = 12, BW_DEL = 18, BW_ACTIVE = 24;
+constexpr int BW_NRED = 12;     // per-CTA partial sums of the backward point pass: Cbar 9, rbar 3
+struct IcpWorkspace {
+  void* packed;        // [N, m_pad] Vec4
+  void* nn_ws;         // split partials of the NN search
+  size_t nn_ws_bytes;
+  double* partials;    // [N, nblk, RED_N]
+  Ctrl* ctrl;
+  double* bw_state;    // [N, BW_STRIDE]
+  double* bw_partials; // [N, nblk, BW_NRED]
+  size_t total;
+};
+IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size);
+
+}  // namespace dicp

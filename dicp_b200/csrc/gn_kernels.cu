@@ -1,0 +1,404 @@
+// gn_kernels.cu — the Gauss-Newton half of the dICP loop and the forward driver.
+//
+//   gn_accum_kernel   per correspondence: gather the neighbour row, residual, point-to-plane
+//                     projection, trim / robust weights, Jacobian row(s), and the 21+6+4
+//                     sums of the normal equations (ICP.py:143-200).  HBM-bound: 48 B per
+//                     correspondence (pt2pl).  Per-thread FP32/FP64 partial sums, warp
+//                     shuffle + shared-memory tree in double, one partial row per CTA.
+//   gn_update_kernel  per pair: fixed-order sum of the CTA partials (deterministic), 6x6
+//                     (3x3 for dim 2) pivoted solve in double, exp-map update of (C, r),
+//                     side outputs, convergence / freeze bookkeeping (ICP.py:200-260).
+//   finalize_kernel   pc = C p + r, T, stats of non-converged pairs (ICP.py:267-292).
+//
+// The iteration loop runs in dicp_icp_forward_*: one launch sequence per iteration, no
+// host synchronisation when const_iter is set, otherwise one flag read every
+// `check_every` iterations (the reference synchronises every iteration, ICP.py:240).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace dicp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_PTS_PER_THREAD = 4;
+
+int gn_blocks_per_pair(int n) {
+  int nb = (n + GN_THREADS * GN_PTS_PER_THREAD - 1) / (GN_THREADS * GN_PTS_PER_THREAD);
+  if (nb < 1) nb = 1;
+  if (nb > 128) nb = 128;
+  return nb;
+}
+
+// block-wide sum of NV per-thread values (in double); result lands in out[0..NV) of the
+// CTA's partial row.  Fixed tree => deterministic for a given launch shape.
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double* vals, double* out, double* smem /* [warps][NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double x = vals[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) smem[warp * NV + v] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += smem[w * NV + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+template <typename T, bool PT2PL, int DIM>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
+                const int32_t* __restrict__ idx, const double* __restrict__ state, int n, int m, int S,
+                WeightParams P, T* __restrict__ weights_out, long long w_pair_stride,
+                double* __restrict__ partials, const int* __restrict__ stop_flag) {
+  if (stop_flag != nullptr && *stop_flag != 0) return;
+  __shared__ double red_smem[(GN_THREADS / 32) * RED_N];
+  const int b = blockIdx.y;
+  const double* rec = state + (size_t)b * ST_STRIDE;
+  T C[9], r[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) C[i] = (T)rec[ST_C + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = (T)rec[ST_R + i];
+  const T active = (T)rec[ST_ACTIVE];
+
+  T acc[RED_N];
+#pragma unroll
+  for (int i = 0; i < RED_N; ++i) acc[i] = T(0);
+
+  const T* src_b = source + (size_t)b * n * 3;
+  const T* tgt_b = target + (size_t)b * m * S;
+  const int32_t* idx_b = idx + (size_t)b * n;
+  constexpr int R = PT2PL ? 1 : 3;
+  T* wout = weights_out != nullptr ? weights_out + (size_t)b * w_pair_stride : nullptr;
+
+  for (int i = blockIdx.x * GN_THREADS + threadIdx.x; i < n; i += gridDim.x * GN_THREADS) {
+    const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
+    const T* row = tgt_b + (size_t)idx_b[i] * S;
+    const T q[3] = {row[0], row[1], row[2]};
+    T nr[3] = {T(0), T(0), T(0)};
+    if (PT2PL) { nr[0] = row[3]; nr[1] = row[4]; nr[2] = row[5]; }
+    const T w0 = (w_init != nullptr ? w_init[(size_t)b * n + i] : T(1)) * active;      // ICP.py:257
+    PointEval<T> s;
+    eval_point<T, PT2PL>(C, r, p, q, nr, w0, P, s);
+    accum_point<T, PT2PL, DIM>(acc, s, w0, P.thresh);
+    if (wout != nullptr) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) wout[(size_t)i * R + k] = s.w;                        // ICP.py:222, 164-165
+    }
+  }
+  double vals[RED_N];
+#pragma unroll
+  for (int i = 0; i < RED_N; ++i) vals[i] = (double)acc[i];
+  block_reduce_store<RED_N>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * RED_N, red_smem);
+}
+
+template <typename T>
+int gn_accumulate(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* state,
+                  int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,
+                  double* partials, const int* stop_flag, cudaStream_t st) {
+  const WeightParams P = make_weight_params(p);
+  dim3 grid(gn_blocks_per_pair(n), N);
+  const bool pl = p->icp_type == DICP_PT2PL;
+#define DICP_GN_LAUNCH(PL, DM) \
+  gn_accum_kernel<T, PL, DM><<<grid, GN_THREADS, 0, st>>>(source, target, w_init, idx, state, n, m, S, P, weights_out, w_pair_stride, partials, stop_flag)
+  if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
+  else if (pl) DICP_GN_LAUNCH(true, 2);
+  else if (p->dim == 3) DICP_GN_LAUNCH(false, 3);
+  else DICP_GN_LAUNCH(false, 2);
+#undef DICP_GN_LAUNCH
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+template int gn_accumulate<float>(const float*, const float*, const float*, const int32_t*, const double*, int, int, int, int,
+                                  const dicp_params*, float*, long long, double*, const int*, cudaStream_t);
+template int gn_accumulate<double>(const double*, const double*, const double*, const int32_t*, const double*, int, int, int, int,
+                                   const dicp_params*, double*, long long, double*, const int*, cudaStream_t);
+
+// sum the CTA partial rows of pair b in a fixed order (thread v sums slot v)
+__device__ __forceinline__ void sum_partials(const double* partials, int b, int nblk, int nslots, double* red) {
+  if ((int)threadIdx.x < nslots) {
+    double s = 0.0;
+    for (int j = 0; j < nblk; ++j) s += partials[((size_t)b * nblk + j) * nslots + threadIdx.x];
+    red[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void init_state_kernel(const T* __restrict__ T_init, int N, double* __restrict__ state0,
+                                  uint8_t* __restrict__ converged, T* __restrict__ num_iters, T* __restrict__ match_ratio) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= N) return;
+  const T* Ti = T_init + (size_t)b * 16;
+  double* rec = state0 + (size_t)b * ST_STRIDE;
+  for (int i = 0; i < ST_STRIDE; ++i) rec[i] = 0.0;
+  for (int rr = 0; rr < 3; ++rr) {
+    for (int c = 0; c < 3; ++c) rec[ST_C + rr * 3 + c] = (double)Ti[rr * 4 + c];       // ICP.py:125
+    rec[ST_R + rr] = (double)Ti[rr * 4 + 3];                                            // ICP.py:126
+  }
+  rec[ST_ACTIVE] = 1.0;
+  converged[b] = 0;
+  num_iters[b] = T(0);
+  match_ratio[b] = T(0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+gn_update_kernel(const double* __restrict__ partials, int nblk, double* __restrict__ state_cur, double* __restrict__ state_nxt,
+                 int k, int dim, int const_iter, double tolerance, T* __restrict__ deltas, T* __restrict__ costs,
+                 T* __restrict__ weights, int K, long long nw, uint8_t* __restrict__ converged,
+                 T* __restrict__ num_iters, T* __restrict__ match_ratio, Ctrl* __restrict__ ctrl, int N) {
+  if (ctrl->stop != 0) return;
+  __shared__ double red[RED_N];
+  __shared__ int s_dead;
+  const int b = blockIdx.x;
+  sum_partials(partials, b, nblk, RED_N, red);
+  if (threadIdx.x == 0) {
+    double* cur = state_cur + (size_t)b * ST_STRIDE;
+    double* nxt = state_nxt + (size_t)b * ST_STRIDE;
+    for (int i = 0; i < ST_STRIDE; ++i) nxt[i] = 0.0;
+    double ni = (double)num_iters[b], mr = (double)match_ratio[b];
+    const double prev_cost = k > 0 ? (double)costs[(size_t)b * K + k - 1] : 0.0;
+    PairOutcome out;
+    pair_update<T>(red, cur, nxt, k, dim, const_iter != 0, tolerance, prev_cost, &ni, &mr, out);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) deltas[((size_t)b * K + k) * 6 + i] = (T)out.delta[i];   // ICP.py:220
+    costs[(size_t)b * K + k] = (T)out.cost;                                              // ICP.py:229-234
+    num_iters[b] = (T)ni;
+    match_ratio[b] = (T)mr;
+    if (out.below) converged[b] = 1;                                                     // ICP.py:239
+    s_dead = out.dead_weights ? 1 : 0;
+    if (out.singular) atomicExch(&ctrl->singular, 1);
+    if (out.below) atomicAdd(&ctrl->nbelow, 1);
+    __threadfence();
+    const int t = atomicAdd(&ctrl->ticket, 1);
+    if (t == N - 1) {                       // last pair of this iteration
+      const int nb = atomicAdd(&ctrl->nbelow, 0);
+      if (!const_iter && nb == N) ctrl->stop = 1;                                        // ICP.py:259-260
+      ctrl->iters_run = k + 1;
+      ctrl->ticket = 0;
+      ctrl->nbelow = 0;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  if (s_dead && weights != nullptr) {                                                    // ICP.py:224-226
+    T* wk = weights + ((size_t)b * K + k) * nw;
+    const T* wp = wk - nw;
+    for (long long i = threadIdx.x; i < nw; i += blockDim.x) wk[i] = wp[i];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+finalize_kernel(const T* __restrict__ source, int n, const double* __restrict__ state_all, int N, const Ctrl* __restrict__ ctrl,
+                double thresh, double rows, T* __restrict__ pc, T* __restrict__ T_out,
+                T* __restrict__ num_iters, T* __restrict__ match_ratio) {
+  const int b = blockIdx.y;
+  const int kr = ctrl->iters_run;
+  const double* after = state_all + ((size_t)kr * N + b) * ST_STRIDE;
+  T C[9], r[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) C[i] = (T)after[ST_C + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = (T)after[ST_R + i];
+  const T* src_b = source + (size_t)b * n * 3;
+  T* pc_b = pc + (size_t)b * n * 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
+    T a[3];
+    rotate(C, p, a);
+    pc_b[3 * i] = a[0] + r[0]; pc_b[3 * i + 1] = a[1] + r[1]; pc_b[3 * i + 2] = a[2] + r[2];   // ICP.py:274
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    T* To = T_out + (size_t)b * 16;                                                      // ICP.py:277-280
+    for (int rr = 0; rr < 3; ++rr) {
+      for (int c = 0; c < 3; ++c) To[rr * 4 + c] = C[rr * 3 + c];
+      To[rr * 4 + 3] = r[rr];
+    }
+    To[12] = T(0); To[13] = T(0); To[14] = T(0); To[15] = T(1);
+    if (kr > 0) {
+      const double* last = state_all + ((size_t)(kr - 1) * N + b) * ST_STRIDE;
+      double ni = (double)num_iters[b], mr = (double)match_ratio[b];
+      final_stats(last, after, kr, thresh, rows, &ni, &mr);                              // ICP.py:267-271
+      num_iters[b] = (T)ni;
+      match_ratio[b] = (T)mr;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// workspace layout of one forward / backward call
+// ---------------------------------------------------------------------------------------
+IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size) {
+  Arena ar(ws, ws_bytes);
+  IcpWorkspace w;
+  w.packed = ar.take<char>((size_t)N * nn_m_pad(m) * 4 * elem_size);
+  w.nn_ws_bytes = nn_search_ws_bytes(N, n, m, elem_size);
+  w.nn_ws = ar.take<char>(w.nn_ws_bytes > 0 ? w.nn_ws_bytes : 1);
+  w.partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * RED_N);
+  w.ctrl = ar.take<Ctrl>(1);
+  w.bw_state = ar.take<double>((size_t)N * BW_STRIDE);
+  w.bw_partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * BW_NRED);
+  w.total = ar.off;
+  return w;
+}
+
+template <typename T>
+static int icp_forward_impl(const T* source, const T* target, const T* T_init, const T* w_init, int N, int n, int m, int S,
+                            const dicp_params* p, T* pc, T* T_out, T* deltas, T* weights, T* costs, uint8_t* converged,
+                            T* num_iters, T* match_ratio, int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
+                            void* ws, size_t ws_bytes, void* stream) {
+  DICP_CHECK_ARG(source && target && T_init && p && pc && T_out && deltas && costs && converged && num_iters && match_ratio &&
+                 saved_idx && saved_state && iters_run_host, "null pointer");
+  DICP_CHECK_ARG(N >= 1 && N <= 65535 && n >= 1 && m >= 1, "need 1 <= N <= 65535, n >= 1, m >= 1");
+  DICP_CHECK_ARG(p->dim == 2 || p->dim == 3, "dim must be 2 or 3");                      // ICP.py:79
+  DICP_CHECK_ARG(p->icp_type == DICP_PT2PL || p->icp_type == DICP_PT2PT, "icp_type must be pt2pl or pt2pt");
+  DICP_CHECK_ARG(p->icp_type != DICP_PT2PL || S == 6, "pt2pl needs a 6-column target");  // ICP.py:103
+  DICP_CHECK_ARG(S == 3 || S == 6, "target must have 3 or 6 columns");
+  DICP_CHECK_ARG(p->loss_id >= 0 && p->loss_id <= 2, "invalid loss id");                 // loss.py:19
+  DICP_CHECK_ARG(p->max_iterations >= 1, "max_iterations must be >= 1");
+  if (ws == nullptr || ws_bytes < plan_workspace(nullptr, 0, N, n, m, sizeof(T)).total) {
+    set_error("dicp_icp_forward: workspace too small");
+    return DICP_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef typename Vec4<T>::type V4;
+  IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T));
+  const int K = p->max_iterations;
+  const bool pl = p->icp_type == DICP_PT2PL;
+  const long long nw = (long long)n * (pl ? 1 : 3);
+  const int nblk = gn_blocks_per_pair(n);
+  const int check_every = p->check_every >= 1 ? p->check_every : 1;
+  const size_t rec_stride = (size_t)N * ST_STRIDE;
+
+  DICP_CUDA(cudaMemsetAsync(w.ctrl, 0, sizeof(Ctrl), st));
+  init_state_kernel<T><<<(N + 127) / 128, 128, 0, st>>>(T_init, N, saved_state, converged, num_iters, match_ratio);
+  DICP_LAUNCH_CHECK();
+  int rc = nn_pack_targets<T>(target, N, m, S, (V4*)w.packed, st);
+  if (rc) return rc;
+
+  Ctrl h;
+  memset(&h, 0, sizeof(h));
+  for (int k = 0; k < K; ++k) {
+    double* rec_k = saved_state + (size_t)k * rec_stride;
+    int32_t* idx_k = saved_idx + (size_t)k * N * n;
+    rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st);
+    if (rc) return rc;
+    rc = gn_accumulate<T>(source, target, w_init, idx_k, rec_k, N, n, m, S, p,
+                          weights != nullptr ? weights + (size_t)k * nw : nullptr, (long long)K * nw, w.partials, &w.ctrl->stop, st);
+    if (rc) return rc;
+    gn_update_kernel<T><<<N, 128, 0, st>>>(w.partials, nblk, rec_k, rec_k + rec_stride, k, p->dim, p->const_iter, p->tolerance,
+                                           deltas, costs, weights, K, nw, converged, num_iters, match_ratio, w.ctrl, N);
+    DICP_LAUNCH_CHECK();
+    if (!p->const_iter && ((k + 1) % check_every == 0) && k + 1 < K) {
+      DICP_CUDA(cudaMemcpyAsync(&h, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+      DICP_CUDA(cudaStreamSynchronize(st));
+      if (h.stop) break;
+    }
+  }
+  dim3 fgrid(gn_blocks_per_pair(n), N);
+  finalize_kernel<T><<<fgrid, 256, 0, st>>>(source, n, saved_state, N, w.ctrl, p->match_ratio_thresh, (double)nw,
+                                            pc, T_out, num_iters, match_ratio);
+  DICP_LAUNCH_CHECK();
+  DICP_CUDA(cudaMemcpyAsync(&h, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  DICP_CUDA(cudaStreamSynchronize(st));
+  *iters_run_host = h.iters_run;
+  if (h.singular) {
+    set_error("dicp_icp_forward: singular normal-equation matrix (torch.linalg.inv would raise, ICP.py:201)");
+    return DICP_ERR_SINGULAR;
+  }
+  return 0;
+}
+
+template <typename T>
+static int gn_accumulate_api(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* C_r,
+                             int N, int n, int m, int S, const dicp_params* p, T* weights_out, double* red_out,
+                             void* ws, size_t ws_bytes, void* stream);
+
+// expands [N,12] (C,r) into saved-state records so the stage API can reuse the loop's kernel
+__global__ void expand_state_kernel(const double* __restrict__ C_r, int N, double* __restrict__ state) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= N) return;
+  double* rec = state + (size_t)b * ST_STRIDE;
+  for (int i = 0; i < ST_STRIDE; ++i) rec[i] = 0.0;
+  for (int i = 0; i < 12; ++i) rec[i] = C_r[(size_t)b * 12 + i];
+  rec[ST_ACTIVE] = 1.0;
+}
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int nblk, double* __restrict__ red_out) {
+  __shared__ double red[RED_N];
+  sum_partials(partials, blockIdx.x, nblk, RED_N, red);
+  if (threadIdx.x < RED_N) red_out[(size_t)blockIdx.x * RED_N + threadIdx.x] = red[threadIdx.x];
+}
+
+template <typename T>
+static int gn_accumulate_api(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* C_r,
+                             int N, int n, int m, int S, const dicp_params* p, T* weights_out, double* red_out,
+                             void* ws, size_t ws_bytes, void* stream) {
+  DICP_CHECK_ARG(source && target && idx && C_r && p && red_out, "null pointer");
+  DICP_CHECK_ARG(N >= 1 && N <= 65535 && n >= 1 && m >= 1 && (S == 3 || S == 6), "bad sizes");
+  DICP_CHECK_ARG(p->icp_type != DICP_PT2PL || S == 6, "pt2pl needs a 6-column target");
+  const int nblk = gn_blocks_per_pair(n);
+  Arena ar(ws, ws_bytes);
+  double* state = ar.take<double>((size_t)N * ST_STRIDE);
+  double* partials = ar.take<double>((size_t)N * nblk * RED_N);
+  if (ws == nullptr || state == nullptr || partials == nullptr) { set_error("dicp_gn_accumulate: workspace too small"); return DICP_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  expand_state_kernel<<<(N + 127) / 128, 128, 0, st>>>(C_r, N, state);
+  DICP_LAUNCH_CHECK();
+  const long long nw = (long long)n * (p->icp_type == DICP_PT2PL ? 1 : 3);
+  int rc = gn_accumulate<T>(source, target, w_init, idx, state, N, n, m, S, p, weights_out, nw, partials, nullptr, st);
+  if (rc) return rc;
+  sum_partials_kernel<<<N, 32, 0, st>>>(partials, nblk, red_out);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dicp
+
+extern "C" {
+int dicp_version(void) { return DICP_VERSION; }
+const char* dicp_last_error(void) { return dicp::g_err; }
+
+size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size) {
+  return dicp::plan_workspace(nullptr, 0, N, n, m, elem_size).total;
+}
+
+int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init, int N, int n, int m,
+                         int S, const dicp_params* params, float* pc, float* T_out, float* deltas, float* weights, float* costs,
+                         uint8_t* converged, float* num_iters, float* match_ratio, int32_t* saved_idx, double* saved_state,
+                         int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream) {
+  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+                                       converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
+}
+int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init, int N, int n,
+                         int m, int S, const dicp_params* params, double* pc, double* T_out, double* deltas, double* weights,
+                         double* costs, uint8_t* converged, double* num_iters, double* match_ratio, int32_t* saved_idx,
+                         double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream) {
+  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+                                        converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
+}
+int dicp_gn_accumulate_f32(const float* source, const float* target, const float* w_init, const int32_t* idx, const double* C_r,
+                           int N, int n, int m, int S, const dicp_params* params, float* weights_out, double* red_out,
+                           void* ws, size_t ws_bytes, void* stream) {
+  return dicp::gn_accumulate_api<float>(source, target, w_init, idx, C_r, N, n, m, S, params, weights_out, red_out, ws, ws_bytes, stream);
+}
+int dicp_gn_accumulate_f64(const double* source, const double* target, const double* w_init, const int32_t* idx, const double* C_r,
+                           int N, int n, int m, int S, const dicp_params* params, double* weights_out, double* red_out,
+                           void* ws, size_t ws_bytes, void* stream) {
+  return dicp::gn_accumulate_api<double>(source, target, w_init, idx, C_r, N, n, m, S, params, weights_out, red_out, ws, ws_bytes, stream);
+}
+}

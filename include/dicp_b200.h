@@ -1,0 +1,153 @@
+/*
+ * dicp_b200.h — C ABI of the B200-native dICP hot path (libdicp_b200.so).
+ *
+ * The reference (utiasASRL/dICP) is pure Python/PyTorch and has no FFI of its own; its
+ * boundary is the Python surface `dICP.ICP.ICP.icp` / `dICP.nn.nn.find_nn`.  The entry
+ * points below are what a reference maintainer would bind (ctypes)
+ * to replace the body of the loop at dICP/ICP.py:132-303 and the search at
+ * dICP/nn.py:23-40.  Each declaration cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *  - tensors are dense, row-major, in the element type of the suffix (_f32 / _f64);
+ *  - functions allocate nothing: the caller passes a workspace sized by the matching
+ *    `*_workspace_bytes` query (256-byte aligned);
+ *  - all work is stream-ordered on `stream` (a cudaStream_t passed as void*);
+ *  - return value: 0 ok, <0 argument error (DICP_ERR_*), >0 a cudaError_t;
+ *    `dicp_last_error()` returns a thread-local message;
+ *  - no C++ exceptions cross the boundary, no static mutable state, thread-safe.
+ */
+#ifndef DICP_B200_H
+#define DICP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DICP_API __attribute__((visibility("default")))
+#else
+#define DICP_API
+#endif
+
+#define DICP_VERSION 100
+
+#define DICP_ERR_ARG       -1   /* bad size / null pointer / unsupported option */
+#define DICP_ERR_WORKSPACE -2   /* workspace too small */
+#define DICP_ERR_SINGULAR  -3   /* a normal-equation matrix was exactly singular
+                                   (the reference's torch.linalg.inv raises, ICP.py:201) */
+
+#define DICP_PT2PL 0            /* icp_type 'pt2pl' (ICP.py:143-146, 172-176) */
+#define DICP_PT2PT 1            /* icp_type 'pt2pt' (ICP.py:147-149, 177-180) */
+
+#define DICP_LOSS_NONE   0      /* loss_fn=None            (ICP.py:157-158) */
+#define DICP_LOSS_HUBER  1      /* loss.py:21-32 */
+#define DICP_LOSS_CAUCHY 2      /* loss.py:34-41 */
+
+/* doubles per (iteration, pair) record in the saved-state buffer, see DESIGN.md §3 */
+#define DICP_STATE_STRIDE 64
+
+/* Everything ICP.__init__ / ICP.dICP / config/dICP_config.yaml fix for one call. */
+typedef struct dicp_params {
+  int32_t icp_type;          /* DICP_PT2PL | DICP_PT2PT              ICP.py:30   */
+  int32_t dim;               /* 2 | 3                                ICP.py:79   */
+  int32_t differentiable;    /* soft (tanh / pseudo-Huber) weights   ICP.py:38   */
+  int32_t loss_id;           /* DICP_LOSS_*                          ICP.py:158  */
+  int32_t use_trim;          /* trim_dist is not None and >= 0       ICP.py:153  */
+  int32_t max_iterations;    /*                                      ICP.py:31   */
+  int32_t const_iter;        /* yaml parameters.const_iter           ICP.py:33   */
+  int32_t check_every;       /* host polls the device "all converged" flag every this
+                                many iterations when !const_iter (>=1; 1 == reference) */
+  double loss_metric;        /* loss_fn['metric']                    ICP.py:159  */
+  double trim_dist;          /*                                      ICP.py:154  */
+  double tanh_steepness;     /* yaml parameters.tanh_steepness       ICP.py:119  */
+  double tolerance;          /*                                      ICP.py:32   */
+  double match_ratio_thresh; /* yaml logging.matched_ratio_thresh    ICP.py:37   */
+} dicp_params;
+
+DICP_API int         dicp_version(void);
+DICP_API const char* dicp_last_error(void);
+
+/* ---- nearest neighbour: replaces cdist + argmin at dICP/nn.py:32-35 (== 83-86) --------
+ * q   [N,n,3]   queries
+ * tgt [N,m,S]   targets, S in {3,6}; only the first 3 columns are used
+ * idx_out [N,n] int32 index of the nearest target (first minimum on exact ties)
+ * d2_out  [N,n] squared distance to it, or NULL
+ * Distances are evaluated in the direct form (x-y)^2 in the element type, so the result
+ * equals the exact-arithmetic argmin whenever the relative gap between the two smallest
+ * squared distances exceeds a few ulp.                                                  */
+DICP_API size_t dicp_nn_workspace_bytes(int N, int n, int m, int elem_size);
+DICP_API int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, int m, int S,
+                       int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, int S,
+                       int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- neighbour gather and its adjoint: replaces repeat+gather at dICP/nn.py:37-38 ------
+ * out[b,i,:] = tgt[b,idx[b,i],:]           grad_tgt[b,idx[b,i],:] += grad_out[b,i,:]
+ * grad_tgt must be zero-initialised by the caller (it is accumulated into).             */
+DICP_API int dicp_gather_rows_f32(const float* tgt, const int32_t* idx, int N, int n, int m, int S, float* out, void* stream);
+DICP_API int dicp_gather_rows_f64(const double* tgt, const int32_t* idx, int N, int n, int m, int S, double* out, void* stream);
+DICP_API int dicp_gather_rows_bwd_f32(const float* grad_out, const int32_t* idx, int N, int n, int m, int S, float* grad_tgt, void* stream);
+DICP_API int dicp_gather_rows_bwd_f64(const double* grad_out, const int32_t* idx, int N, int n, int m, int S, double* grad_tgt, void* stream);
+
+/* ---- the whole solver loop: replaces dICP/ICP.py:125-303 -------------------------------
+ * inputs  source [N,n,3], target [N,m,S] (S=6 for pt2pl, 3 or 6 for pt2pt),
+ *         T_init [N,4,4], w_init [N,n] (per point; pt2pt's x3 repeat is implicit)
+ * outputs pc [N,n,3], T [N,4,4],
+ *         deltas  [N,K,6]        K = max_iterations rows are allocated; the first
+ *         weights [N,K,n*R]      *iters_run_host are valid (R = 1 pt2pl, 3 pt2pt)
+ *         costs   [N,K]
+ *         converged [N] uint8, num_iters [N], match_ratio [N]      (ICP.py:288-292)
+ * saved   saved_idx   [K,N,n] int32   correspondences of every iteration
+ *         saved_state [(K+1),N,DICP_STATE_STRIDE] double  (C_k,r_k,active,delta_k,A_k ...)
+ * iters_run_host: host int32, written before return (the call synchronises the stream
+ *         once at its end, and every check_every iterations when !const_iter).          */
+DICP_API size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size);
+DICP_API int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init,
+                         int N, int n, int m, int S, const dicp_params* params,
+                         float* pc, float* T_out, float* deltas, float* weights, float* costs,
+                         uint8_t* converged, float* num_iters, float* match_ratio,
+                         int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
+                         void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init,
+                         int N, int n, int m, int S, const dicp_params* params,
+                         double* pc, double* T_out, double* deltas, double* weights, double* costs,
+                         uint8_t* converged, double* num_iters, double* match_ratio,
+                         int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ---- reverse pass: replaces torch autograd through ICP.py:132-280 -----
+ * grad_T [N,4,4], grad_pc [N,n,3] (either may be NULL == zero)
+ * grad_source [N,n,3], grad_target [N,m,S], grad_w [N,n] (may be NULL), grad_T_init [N,4,4]
+ * are overwritten.  iters_run is the value the forward returned.                        */
+DICP_API int dicp_icp_backward_f32(const float* source, const float* target, const float* w_init,
+                          int N, int n, int m, int S, const dicp_params* params, int iters_run,
+                          const int32_t* saved_idx, const double* saved_state,
+                          const float* grad_T, const float* grad_pc,
+                          float* grad_source, float* grad_target, float* grad_w, float* grad_T_init,
+                          void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_icp_backward_f64(const double* source, const double* target, const double* w_init,
+                          int N, int n, int m, int S, const dicp_params* params, int iters_run,
+                          const int32_t* saved_idx, const double* saved_state,
+                          const double* grad_T, const double* grad_pc,
+                          double* grad_source, double* grad_target, double* grad_w, double* grad_T_init,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ---- single Gauss-Newton stages, exported for tests and profiling ----------------------
+ * One iteration's accumulate (ICP.py:143-200) on given correspondences: red_out [N,32]
+ * doubles = upper-triangular A (21 | 6), b (6 | 3) at 21.., cost at 27, sum(w) 28,
+ * #(w>thresh) 29, #(w_init>thresh) 30.  C_r [N,12] = row-major C then r, in double.     */
+DICP_API int dicp_gn_accumulate_f32(const float* source, const float* target, const float* w_init, const int32_t* idx,
+                           const double* C_r, int N, int n, int m, int S, const dicp_params* params,
+                           float* weights_out, double* red_out, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_gn_accumulate_f64(const double* source, const double* target, const double* w_init, const int32_t* idx,
+                           const double* C_r, int N, int n, int m, int S, const dicp_params* params,
+                           double* weights_out, double* red_out, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DICP_B200_H */

@@ -1,0 +1,323 @@
+"""GPU parity tests: the CUDA path, called through the public API and the C ABI, against the
+oracle (oracle/) and the golden vectors of the unmodified reference (tests/golden/)."""
+import numpy as np
+import pytest
+import torch
+
+from cases import DENSE_CASES, FIXTURE_CASES, golden_loss
+from helpers import load_golden, rel_err, se3_log, T_ts_true, tt
+
+pytestmark = pytest.mark.gpu
+
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+def _icp(icp_type, diff, max_it, tol, const_iter=False, check_every=1):
+    from dICP.ICP import ICP
+    icp = ICP(icp_type=icp_type, differentiable=diff, max_iterations=max_it, tolerance=tol)
+    icp.const_iter = const_iter
+    icp.check_every = check_every
+    return icp
+
+
+def _check(res, g, tol):
+    assert res["deltas"].shape == g["deltas"].shape, "iteration count differs"
+    assert res["weights"].shape == g["weights"].shape and res["costs"].shape == g["costs"].shape
+    assert rel_err(res["T"].detach().cpu(), g["T"]) < tol
+    assert rel_err(res["pc"].detach().cpu(), g["pc"]) < tol
+    assert np.abs(res["deltas"].cpu().numpy() - g["deltas"]).max() < tol * max(1.0, np.abs(g["deltas"]).max())
+    assert rel_err(res["weights"].cpu(), g["weights"]) < tol
+    assert rel_err(res["costs"].cpu(), g["costs"]) < 10 * tol
+    st = res["stats"]
+    assert st["converged"].dtype == torch.bool
+    assert np.array_equal(st["converged"].cpu().numpy(), g["converged"])
+    assert np.array_equal(st["iterations"].cpu().numpy(), g["iterations"])
+    assert np.allclose(st["matched_ratio"].cpu().numpy(), g["matched_ratio"], rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+@pytest.mark.parametrize("case", FIXTURE_CASES, ids=[c[0] for c in FIXTURE_CASES])
+def test_fixture_cases(case, device):
+    """Reference fixture workloads (tests/test_ICP.py, BASELINE config 1), fp64, dim=2.
+    device='cpu' exercises the host-buffer path (inputs staged through the GPU)."""
+    name, icp_type, diff, lname, metric, trim, max_it, tol, szap = case
+    g = load_golden(name)
+    src = tt(g["source"]).to(device).requires_grad_(True)
+    tgt = tt(g["target"]).to(device).requires_grad_(True)
+    T0 = tt(g["T_init"]).to(device).requires_grad_(True)
+    icp = _icp(icp_type, diff, max_it, tol)
+    icp.source_zeroes_are_pad = szap
+    loss_fn = {"name": lname, "metric": metric} if lname else None
+    res = icp.icp(src, tgt, T0, trim_dist=trim, loss_fn=loss_fn, dim=2)
+    assert res["T"].device.type == device and res["T"].dtype == torch.float64
+    _check(res, g, 1e-9)
+    golden_loss(res).backward()
+    assert src.grad is not None and tgt.grad is not None and T0.grad is not None
+    assert not torch.isnan(src.grad).any() and not torch.isnan(tgt.grad).any()
+    if np.isnan(g["g_source"]).any():
+        return      # reference autograd is NaN here (hard Huber, zero residual); ours is finite by design
+    ns = g["g_source"].shape[0]
+    assert rel_err(src.grad[:ns].cpu(), g["g_source"]) < 1e-7
+    assert rel_err(tgt.grad.cpu(), g["g_target"]) < 1e-7
+    assert rel_err(T0.grad.cpu(), g["g_T_init"]) < 1e-7
+
+
+def test_fixture_known_answer():
+    """tests/test_ICP.py:65-69 — ||log(T_true T_pred^-1)|| < 1e-10 and pc == target."""
+    for name, icp_type, lname, metric in (("fix_pt2pt_diff_huber", "pt2pt", "huber", 1.0),
+                                          ("fix_pt2pl_diff_huber", "pt2pl", "huber", 10.0),
+                                          ("fix_pt2pl_diff_cauchy", "pt2pl", "cauchy", 0.5)):
+        g = load_golden(name)
+        src, tgt = tt(g["source"]).cuda(), tt(g["target"]).cuda()
+        res = _icp(icp_type, True, 100, 1e-10).icp(src, tgt, torch.eye(4, dtype=src.dtype, device="cuda"), trim_dist=5.0,
+                                                   loss_fn={"name": lname, "metric": metric}, dim=2)
+        xi = se3_log(T_ts_true() @ np.linalg.inv(res["T"][0].cpu().numpy()))
+        assert np.linalg.norm(xi) < 1e-10
+        assert np.allclose(res["pc"][0].cpu().numpy(), g["target"][:, :3], atol=1e-5)
+
+
+@pytest.mark.parametrize("case", DENSE_CASES, ids=[c[0] for c in DENSE_CASES])
+def test_dense_cases(case):
+    """Seeded synthetic dim=3 workloads, fp64 and fp32, with user weights and a non-identity T_init."""
+    name, icp_type, diff, lname, metric, trim, K, const_iter, tol, out_tol, grad_tol = case
+    g = load_golden(name)
+    src = tt(g["source"]).cuda().requires_grad_(True)
+    tgt = tt(g["target"]).cuda().requires_grad_(True)
+    T0 = tt(g["T_init"]).cuda().requires_grad_(True)
+    w = tt(g["weight"]).cuda().requires_grad_(True) if "weight" in g else None
+    icp = _icp(icp_type, diff, K, tol, const_iter=const_iter)
+    loss_fn = {"name": lname, "metric": metric} if lname else None
+    res = icp.icp(src, tgt, T0, weight=w, trim_dist=trim, loss_fn=loss_fn, dim=3)
+    _check(res, g, out_tol)
+    golden_loss(res).backward()
+    assert rel_err(src.grad.cpu(), g["g_source"]) < grad_tol
+    assert rel_err(tgt.grad.cpu(), g["g_target"]) < grad_tol
+    assert rel_err(T0.grad.cpu(), g["g_T_init"]) < grad_tol
+    if w is not None:
+        assert rel_err(w.grad.cpu(), g["g_weight"]) < grad_tol
+
+
+def test_check_every_and_const_iter_shapes():
+    """Early stop changes K (ICP.py:259-260); polling the flag less often must not change results."""
+    g = load_golden("dense_pt2pt_plain_earlystop_f64")
+    src, tgt, T0 = tt(g["source"]).cuda(), tt(g["target"]).cuda(), tt(g["T_init"]).cuda()
+    outs = []
+    for ce in (1, 3, 64):
+        res = _icp("pt2pt", True, 40, 1e-9, check_every=ce).icp(src, tgt, T0, dim=3)
+        _check(res, g, 1e-9)
+        outs.append(res["T"])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    res = _icp("pt2pt", True, 9, 1e-9, const_iter=True).icp(src, tgt, T0, dim=3)
+    assert res["deltas"].shape == (3, 9, 6, 1) and res["weights"].shape == (3, 9, 600, 1) and res["costs"].shape == (3, 9, 1)
+    assert (res["stats"]["iterations"] == 9).all()
+
+
+def test_ragged_list_batch_matches_reference():
+    """tests/test_ICP_inputs.py:36-110 — ragged list batch, padding, frozen pairs, matched ratio."""
+    g = load_golden("ragged_pt2pl")
+    s = [tt(g["s1"]).cuda(), tt(g["s2"]).cuda().requires_grad_(True), tt(g["s3"]).cuda().requires_grad_(True)]
+    t = [tt(g[k]).cuda().requires_grad_(True) for k in ("t1", "t2", "t3")]
+    T0 = torch.eye(4, dtype=torch.float64, device="cuda").repeat(3, 1, 1)
+    icp = _icp("pt2pl", True, 25, 1e-8)
+    padded = icp.batch_size_handling(s, t, T0, None)
+    assert np.array_equal(padded[0].detach().cpu().numpy(), g["pad_source"])
+    assert np.array_equal(padded[1].detach().cpu().numpy(), g["pad_target"])
+    assert np.array_equal(padded[3].detach().cpu().numpy(), g["pad_w"])
+    res = icp.icp(s, t, T0, trim_dist=5.0, loss_fn={"name": "huber", "metric": 1.0}, dim=2)
+    _check(res, g, 1e-9)
+    (res["T"][:, :3, :] * torch.arange(1, 13, dtype=torch.float64, device="cuda").reshape(3, 4)).sum().backward()
+    for ten, key in ((s[1], "g_s2"), (s[2], "g_s3"), (t[0], "g_t1"), (t[1], "g_t2"), (t[2], "g_t3")):
+        assert rel_err(ten.grad.cpu(), g[key]) < 1e-7
+
+
+def test_weight_list_matches_reference():
+    """tests/test_ICP_inputs.py:157-211 with non-trivial weights and their gradient."""
+    g = load_golden("weights_pt2pl")
+    s1 = tt(g["s1"]).cuda().requires_grad_(True)
+    s3 = tt(g["s3"]).cuda().requires_grad_(True)
+    t = tt(g["t"]).cuda().requires_grad_(True)
+    w2 = tt(g["w2"]).cuda().requires_grad_(True)
+    w3 = tt(g["w3"]).cuda().requires_grad_(True)
+    T0 = torch.eye(4, dtype=torch.float64, device="cuda").repeat(3, 1, 1)
+    res = _icp("pt2pl", True, 25, 1e-8).icp([s1, s1, s3], [t, t, t], T0, weight=[None, w2, w3], trim_dist=5.0,
+                                             loss_fn={"name": "huber", "metric": 1.0}, dim=2)
+    _check(res, g, 1e-9)
+    (res["T"][:, :3, :] * torch.arange(1, 13, dtype=torch.float64, device="cuda").reshape(3, 4)).sum().backward()
+    for ten, key in ((s1, "g_s1"), (s3, "g_s3"), (t, "g_t"), (w2, "g_w2"), (w3, "g_w3")):
+        assert rel_err(ten.grad.cpu(), g[key]) < 1e-7
+
+
+def test_zero_inputs_match_reference():
+    g = load_golden("zero_inputs")
+    fx = load_golden("fixture_clouds")
+    s, t = tt(fx["scan"]).cuda(), tt(fx["map"]).cuda()
+    T0 = torch.eye(4, dtype=torch.float64, device="cuda").repeat(3, 1, 1)
+    res = _icp("pt2pl", True, 25, 1e-8).icp([s, [], []], [[], t, []], T0, trim_dist=5.0, loss_fn=None, dim=2)
+    _check(res, g, 1e-12)
+
+
+# ---------------------------------------------------------------------------------------
+# nearest neighbour through the C ABI
+# ---------------------------------------------------------------------------------------
+def _nn_check(x, y, min_ok=1.0):
+    """indices == fp64-exact argmin on tie-free queries (relative gap rule)."""
+    from dicp_b200._functions import nn_argmin
+    from oracle.dicp_oracle import nn_index_exact
+    idx, d2 = nn_argmin(x.cuda(), y.cuda(), return_d2=True)
+    ref, best, second = nn_index_exact(x, y[:, :, :3])
+    eps = EPS32 if x.dtype == torch.float32 else float(np.finfo(np.float64).eps)
+    tie_free = (second - best) > 8 * eps * best
+    got = idx.cpu().long()
+    assert tie_free.float().mean().item() >= min_ok - 1e-3
+    assert torch.equal(got[tie_free], ref[tie_free])
+    # on ties the returned point must still be a nearest one within rounding
+    dsel = ((x.double() - torch.gather(y[:, :, :3].double(), 1, got.unsqueeze(-1).expand(-1, -1, 3))) ** 2).sum(-1)
+    assert (dsel <= best * (1 + 16 * eps) + 1e-300).all()
+    assert torch.allclose(d2.cpu().double(), dsel, rtol=8 * eps, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 7, 1), (3, 65, 65), (2, 1000, 37), (1, 513, 2049), (5, 300, 4097),
+                                   (64, 130, 700), (2, 4096, 4096)])
+def test_nn_random_clouds(shape, dtype):
+    N, n, m = shape
+    gen = torch.Generator().manual_seed(n * 7 + m)
+    x = (torch.rand((N, n, 3), generator=gen, dtype=torch.float64) * 40 - 20).to(dtype)
+    y = (torch.rand((N, m, 6), generator=gen, dtype=torch.float64) * 40 - 20).to(dtype)
+    _nn_check(x, y)
+
+
+def test_nn_first_minimum_on_exact_ties():
+    """duplicated targets: torch.argmin returns the first (nn.py:35)."""
+    from dicp_b200._functions import nn_argmin
+    gen = torch.Generator().manual_seed(1)
+    base = torch.rand((2, 50, 3), generator=gen)
+    y = torch.cat((base, base, base), dim=1)                  # every target appears 3 times
+    x = base[:, torch.randperm(50, generator=gen)] + 0.001
+    idx = nn_argmin(x.cuda(), y.cuda()).cpu().long()
+    ref = torch.argmin(((x[:, :, None, :].double() - y[:, None, :, :].double()) ** 2).sum(-1), dim=2)
+    assert torch.equal(idx, ref) and (idx < 50).all()
+
+
+def test_nn_bench_generator_16k():
+    """the benchmark's wavy-surface pair at 16k x 16k, 2 pairs."""
+    from oracle.dicp_oracle import make_wavy_pair
+    src, tgt = make_wavy_pair(2, 16384, 16384, seed=3000, dtype=torch.float32)
+    _nn_check(src, tgt, min_ok=0.999)
+
+
+def test_nn_known_answers_and_find_nn_api():
+    """tests/test_nn.py:12-41 on the hard-NN path, plus layouts and the gather gradient."""
+    from dICP.nn import nn
+    g = load_golden("nn_known_answers")
+    hard = nn(differentiable=True, use_gumbel=False)
+    pts = tt(g["pts"]).cuda().requires_grad_(True)
+    q = tt(g["q"]).cuda().requires_grad_(True)
+    out = hard.find_nn(q, pts)
+    assert torch.all(out == torch.tensor((8.0, 7.0, 0.0), device="cuda"))
+    out.sum().backward()
+    assert pts.grad is not None and not torch.isnan(pts.grad).any()
+    out2 = hard.find_nn(q, tt(g["pts2"]).cuda())
+    assert torch.all(out2 == torch.tensor((10.0, 2.0, 0.0), device="cuda"))
+    y = tt(g["y"]).cuda().requires_grad_(True)
+    o = nn(differentiable=False).find_nn(tt(g["x"]).cuda(), y)
+    assert np.array_equal(o.detach().cpu().numpy(), g["out"])
+    (o * tt(g["gw"]).cuda()).sum().backward()
+    assert np.allclose(y.grad.cpu().numpy(), g["g_y"], rtol=1e-12, atol=1e-12)
+    o_cf = hard.find_nn(tt(g["x"]).cuda().transpose(1, 2), tt(g["y"]).cuda())     # channel-first query
+    assert np.array_equal(o_cf.cpu().numpy(), g["out"])
+    o_cpu = hard.find_nn(tt(g["x"]), tt(g["y"]))                                    # host buffers
+    assert o_cpu.device.type == "cpu" and np.array_equal(o_cpu.numpy(), g["out"])
+    # default constructor = Gumbel path (stochastic, tau=0.1): the reference test's own assertion
+    soft = nn(differentiable=True).find_nn(tt(g["q"]).cuda(), tt(g["pts"]).cuda())
+    assert torch.all(soft == torch.tensor((8.0, 7.0, 0.0), device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------
+# fp32 at benchmark-like sizes vs the oracle with pinned correspondences
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
+def test_fp32_4096_vs_oracle_pinned(icp_type):
+    """Tolerances of BASELINE.json: T within 1e-5 relative, gradients within 1e-4 relative,
+    against the fp64 oracle replaying the CUDA path's correspondences."""
+    from dicp_b200 import _functions
+    from oracle.dicp_oracle import IcpSettings, icp_forward, make_wavy_pair, nn_index_exact
+    N, n, K = 3, 4096, 10
+    src, tgt = make_wavy_pair(N, n, n, seed=2000, dtype=torch.float32, with_normals=True)
+    if icp_type == "pt2pt":
+        tgt = tgt[:, :, :3].contiguous()
+    icp = _icp(icp_type, True, K, 1e-12, const_iter=True)
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1).requires_grad_(True)
+    res = icp.icp(s, t, T0, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+    wT = torch.arange(1, 13, dtype=torch.float32, device="cuda").reshape(3, 4)
+    (res["T"][:, :3, :] * wT).sum().backward()
+    # recover the correspondences the CUDA path used from its saved state via a second NN call per iteration
+    # (same kernel, same inputs => same indices); here we simply recompute them from the per-iteration transforms
+    idx_list = []
+    C = torch.eye(3, dtype=torch.float64).repeat(N, 1, 1)
+    r = torch.zeros((N, 3, 1), dtype=torch.float64)
+    deltas = res["deltas"].detach().cpu().double()
+    from oracle.adjoint import so3_exp
+    Cf, rf = torch.eye(3).repeat(N, 1, 1), torch.zeros((N, 3, 1))
+    mism = 0
+    for k in range(K):
+        x = (Cf @ src.transpose(1, 2) + rf).transpose(1, 2).contiguous()
+        idx = _functions.nn_argmin(x.cuda(), t.detach()).cpu().long()
+        ref, best, second = nn_index_exact(x, tgt[:, :, :3])
+        tie_free = (second - best) > 8 * EPS32 * best
+        mism += int((idx[tie_free] != ref[tie_free]).sum())
+        idx_list.append(idx)
+        R = so3_exp(deltas[:, k, :3, 0]).float()
+        Cf = R.transpose(1, 2) @ Cf
+        rf = rf - deltas[:, k, 3:, :].float()
+    assert mism == 0
+    cfg = IcpSettings(icp_type=icp_type, max_iterations=K, tolerance=1e-12, const_iter=True, trim_dist=2.0,
+                      loss_name="cauchy", loss_metric=0.5, dim=3)
+    s64 = src.double().requires_grad_(True)
+    t64 = tgt.double().requires_grad_(True)
+    T64 = torch.eye(4, dtype=torch.float64).repeat(N, 1, 1).requires_grad_(True)
+    w64 = torch.ones((N, n * (3 if icp_type == "pt2pt" else 1)), dtype=torch.float64)
+    ref = icp_forward(s64, t64, T64, w64, cfg, replay_idx=idx_list)
+    (ref["T"][:, :3, :] * wT.cpu().double()).sum().backward()
+    assert rel_err(res["T"].detach().cpu(), ref["T"].detach()) < 1e-5
+    assert rel_err(res["pc"].detach().cpu(), ref["pc"].detach()) < 1e-5
+    assert rel_err(s.grad.cpu(), s64.grad) < 1e-4
+    assert rel_err(t.grad.cpu(), t64.grad) < 1e-4
+    assert rel_err(T0.grad.cpu(), T64.grad) < 1e-4
+
+
+def test_gn_accumulate_stage_vs_oracle():
+    """dicp_gn_accumulate_* (ICP.py:143-200) on given correspondences vs explicit fp64 sums."""
+    import ctypes
+    from dicp_b200 import _lib, _functions
+    from oracle.dicp_oracle import make_wavy_pair
+    from oracle.adjoint import icp_forward_saved
+    from oracle.dicp_oracle import IcpSettings
+    lib = _lib.load_library()
+    N, n, m = 4, 5000, 3000
+    src, tgt = make_wavy_pair(N, n, m, seed=77, dtype=torch.float64)
+    idx = _functions.nn_argmin(src.cuda(), tgt.cuda())
+    cfg = IcpSettings(icp_type="pt2pl", max_iterations=1, const_iter=True, trim_dist=2.0, loss_name="cauchy", loss_metric=0.5, dim=3)
+    T0 = torch.eye(4, dtype=torch.float64).repeat(N, 1, 1)
+    fw = icp_forward_saved(src, tgt, T0, torch.ones((N, n), dtype=torch.float64), cfg, [idx.cpu()])
+    A_ref = fw["saved"]["A"][0] - 1e-12 * torch.eye(6, dtype=torch.float64)
+    for dt, tol in ((torch.float64, 1e-12), (torch.float32, 2e-5)):
+        p = _functions.make_params("pt2pl", 3, True, "cauchy", 0.5, 2.0, 5.0, 1e-12, 1, True, 0.0)
+        s_d, t_d = src.to(dt).cuda(), tgt.to(dt).cuda()
+        C_r = torch.cat((torch.eye(3, dtype=torch.float64).reshape(1, 9).repeat(N, 1), torch.zeros((N, 3), dtype=torch.float64)), 1).cuda()
+        red = torch.empty((N, 32), dtype=torch.float64, device="cuda")
+        wout = torch.empty((N, n), dtype=dt, device="cuda")
+        ws = torch.empty(lib.dicp_icp_workspace_bytes(N, n, m, s_d.element_size()) + (1 << 20), dtype=torch.uint8, device="cuda")
+        rc = getattr(lib, "dicp_gn_accumulate_" + _lib.suffix(dt))(
+            _lib.ptr(s_d), _lib.ptr(t_d), None, _lib.ptr(idx), _lib.ptr(C_r), N, n, m, 6, ctypes.byref(p), _lib.ptr(wout),
+            _lib.ptr(red), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_d.device))
+        _lib.check(rc, "gn_accumulate")
+        red = red.cpu()
+        A = torch.zeros((N, 6, 6), dtype=torch.float64)
+        iu = torch.triu_indices(6, 6)
+        A[:, iu[0], iu[1]] = red[:, :21]
+        A = A + A.transpose(1, 2) - torch.diag_embed(torch.diagonal(A, dim1=1, dim2=2))
+        assert rel_err(A, A_ref) < tol
+        assert (red[:, 29] == n).all() and (red[:, 30] == n).all()
