@@ -36,9 +36,12 @@ _SIGNATURES = {
     "dicp_last_error": ([], ctypes.c_char_p),
     "dicp_nn_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),
+    "dicp_nn_packed_bytes": ([_I, _I, _I], _Z),
 }
 for _s in ("f32", "f64"):
     _SIGNATURES["dicp_nn_argmin_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
+    _SIGNATURES["dicp_nn_pack_" + _s] = ([_P, _I, _I, _I, _P, _P], _I)
+    _SIGNATURES["dicp_nn_scan_" + _s] = ([_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_gather_rows_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)
     _SIGNATURES["dicp_gather_rows_bwd_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)
     _SIGNATURES["dicp_icp_forward_" + _s] = ([_P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams),

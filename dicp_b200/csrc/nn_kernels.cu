@@ -303,6 +303,25 @@ int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, 
                        void* ws, size_t ws_bytes, void* stream) {
   return dicp::nn_argmin_impl<double>(q, tgt, N, n, m, S, idx_out, d2_out, ws, ws_bytes, stream);
 }
+size_t dicp_nn_packed_bytes(int N, int m, int elem_size) { return dicp::align_up((size_t)N * dicp::nn_m_pad(m) * 4 * elem_size); }
+int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream) {
+  DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
+  return dicp::nn_pack_targets<float>(tgt, N, m, S, (float4*)packed, (cudaStream_t)stream);
+}
+int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void* stream) {
+  DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
+  return dicp::nn_pack_targets<double>(tgt, N, m, S, (double4*)packed, (cudaStream_t)stream);
+}
+int dicp_nn_scan_f32(const float* q, const void* packed, int N, int n, int m, int32_t* idx_out, float* d2_out, void* ws,
+                     size_t ws_bytes, void* stream) {
+  DICP_CHECK_ARG(q && packed && idx_out && N >= 1 && n >= 1 && m >= 1, "bad arguments");
+  return dicp::nn_search<float>(q, nullptr, (const float4*)packed, N, n, m, idx_out, d2_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+int dicp_nn_scan_f64(const double* q, const void* packed, int N, int n, int m, int32_t* idx_out, double* d2_out, void* ws,
+                     size_t ws_bytes, void* stream) {
+  DICP_CHECK_ARG(q && packed && idx_out && N >= 1 && n >= 1 && m >= 1, "bad arguments");
+  return dicp::nn_search<double>(q, nullptr, (const double4*)packed, N, n, m, idx_out, d2_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
 int dicp_gather_rows_f32(const float* tgt, const int32_t* idx, int N, int n, int m, int S, float* out, void* stream) {
   return dicp::gather_impl<float>(tgt, idx, N, n, m, S, out, stream, false);
 }

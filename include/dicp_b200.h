@@ -85,6 +85,18 @@ DICP_API int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, 
 DICP_API int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, int S,
                        int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
 
+/* The two stages of dicp_nn_argmin_*, exported for profiling and for callers that search the
+ * same targets repeatedly (the solver loop packs once per call): pack the targets into
+ * 16-byte (x,y,z,0) records padded to a multiple of 16 (`dicp_nn_packed_bytes` bytes), then
+ * scan.  `ws` for the scan is sized by dicp_nn_workspace_bytes.                           */
+DICP_API size_t dicp_nn_packed_bytes(int N, int m, int elem_size);
+DICP_API int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream);
+DICP_API int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void* stream);
+DICP_API int dicp_nn_scan_f32(const float* q, const void* packed, int N, int n, int m,
+                     int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_nn_scan_f64(const double* q, const void* packed, int N, int n, int m,
+                     int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- neighbour gather and its adjoint: replaces repeat+gather at dICP/nn.py:37-38 ------
  * out[b,i,:] = tgt[b,idx[b,i],:]           grad_tgt[b,idx[b,i],:] += grad_out[b,i,:]
  * grad_tgt must be zero-initialised by the caller (it is accumulated into).             */

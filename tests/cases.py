@@ -32,8 +32,8 @@ DENSE_CASES = [
 def golden_loss_grads(T, pc):
     """d/dT and d/dpc of the loss make_golden.py back-propagated (loss_of)."""
     gT = torch.zeros_like(T)
-    gT[:, :3, :] = torch.arange(1, 13, dtype=T.dtype).reshape(3, 4)
-    wp = torch.linspace(-1.0, 1.0, pc.shape[1] * 3, dtype=pc.dtype).reshape(pc.shape[1], 3)
+    gT[:, :3, :] = torch.arange(1, 13, dtype=T.dtype, device=T.device).reshape(3, 4)
+    wp = torch.linspace(-1.0, 1.0, pc.shape[1] * 3, dtype=pc.dtype).reshape(pc.shape[1], 3).to(pc.device)
     gpc = (0.01 * wp).expand_as(pc).contiguous()
     return gT, gpc
 

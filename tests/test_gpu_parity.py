@@ -143,8 +143,11 @@ def test_weight_list_matches_reference():
                                              loss_fn={"name": "huber", "metric": 1.0}, dim=2)
     _check(res, g, 1e-9)
     (res["T"][:, :3, :] * torch.arange(1, 13, dtype=torch.float64, device="cuda").reshape(3, 4)).sum().backward()
-    for ten, key in ((s1, "g_s1"), (s3, "g_s3"), (t, "g_t"), (w2, "g_w2"), (w3, "g_w3")):
+    for ten, key in ((s1, "g_s1"), (s3, "g_s3"), (t, "g_t")):
         assert rel_err(ten.grad.cpu(), g[key]) < 1e-7
+    # at the converged, zero-residual solution d T / d weight vanishes: both sides are rounding noise
+    for ten, key in ((w2, "g_w2"), (w3, "g_w3")):
+        assert np.abs(g[key]).max() < 1e-12 and ten.grad.abs().max().item() < 1e-12
 
 
 def test_zero_inputs_match_reference():
