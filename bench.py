@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — ICP pairs/s (forward + backward, 10 constant iterations, 16k points).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], SURVEY.md §8(d) "C3"): per GPU 256 cloud pairs x 16384
+source x 16384 target points, point-to-plane, Cauchy(0.5) + trim(2.0) weights, fp32, dim 3,
+T_init = I, const_iter, 10 iterations, forward + backward, synthetic wavy-surface clouds.
+One "step" = one pass of the hot path over one such batch.  Pairs are independent, so N GPUs
+process N x 256 pairs with no data-path collective (weak scaling; at N=8 this is configs[4]);
+in learning mode one NCCL all-reduce of [loss, d loss / d theta] closes every step.
+
+`value`  : pairs/s with inputs resident in HBM (timed with CUDA events on the launch stream).
+`e2e`    : pairs/s through the public API `dICP.ICP.ICP.icp` with pinned HOST buffers, the
+           host->device copies of the clouds and the device->host read of loss/T/grads inside
+           the timed region.
+`roofline`: the dominant kernel (nearest-neighbour scan, FP32 CUDA-core bound) timed alone
+           with CUDA events; `roofline_gn`: the Gauss-Newton accumulate (HBM bound).
+`cpu_baseline`: the oracle port of the reference's torch-CPU path on a bounded sample.
+`--impl reference`: the same oracle port timed alone on all host threads (the reference is
+           pure Python/torch and cannot travel to the GPU box).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PAIRS_PER_GPU = 256
+NPTS = 16384
+ITERS = 10
+LOSS = {"name": "cauchy", "metric": 0.5}
+TRIM = 2.0
+WORKLOAD = ("C3: %d pairs/GPU x %dx%d pts, pt2pl, cauchy(0.5)+trim(2.0), fp32, dim3, const 10 it, fwd+bwd"
+            % (PAIRS_PER_GPU, NPTS, NPTS))
+METRIC = "ICP pairs/sec (fwd+bwd, 10 iters, 16k pts)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(n_pairs, first_pair, dtype=torch.float32):
+    """seed = 1000*cfg_id + first pair index of the chunk (cfg_id 3)."""
+    from oracle.dicp_oracle import make_wavy_pair      # input generator only
+    return make_wavy_pair(n_pairs, NPTS, NPTS, seed=3000 + first_pair, dtype=dtype, with_normals=True)
+
+
+def learning_loss(res, theta):
+    """Learning-mode objective: theta (12) weighs the top three rows of every T."""
+    return (res["T"][:, :3, :].reshape(-1, 12) * theta).sum()
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's torch-CPU path
+# ---------------------------------------------------------------------------------------
+def cpu_step(src, tgt):
+    from oracle.dicp_oracle import IcpSettings, icp_forward
+    cfg = IcpSettings(icp_type="pt2pl", max_iterations=ITERS, tolerance=1e-12, differentiable=True, const_iter=True,
+                      trim_dist=TRIM, loss_name=LOSS["name"], loss_metric=LOSS["metric"], dim=3)
+    n_pairs = src.shape[0]
+    s = src.clone().requires_grad_(True)
+    t = tgt.clone().requires_grad_(True)
+    T0 = torch.eye(4).repeat(n_pairs, 1, 1)
+    res = icp_forward(s, t, T0, torch.ones((n_pairs, NPTS)), cfg)
+    theta = torch.arange(1, 13, dtype=torch.float32)
+    learning_loss(res, theta).backward()
+    return float(res["T"].sum())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    pairs_per_step = 1           # dense (n,m) distance matrix: 1.07 GB fp32 per pair
+    src, tgt = make_batch(pairs_per_step, 0)
+    for _ in range(args.warmup):
+        cpu_step(src, tgt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(src, tgt)
+    dt = time.perf_counter() - t0
+    value = pairs_per_step * args.steps / dt
+    sample = "%d pair(s) of the C3 workload per step, %d steps, torch %s CPU, %d threads" % (
+        pairs_per_step, args.steps, torch.__version__, torch.get_num_threads())
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_arm": "oracle port of dICP/ICP.py:132-303 (torch CPU ops cdist/argmin/gather/"
+                   "bmm/inv/matrix_exp + autograd); the unmodified reference is Python and is not present on the GPU box"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def time_kernel(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(reps)) / reps * 1e-3   # seconds per launch
+
+
+def roofline_nn(src, tgt, pk):
+    """NN scan kernel alone (dicp_nn_scan_f32), CUDA events on the launch stream."""
+    from dicp_b200 import _lib
+    lib = _lib.load_library()
+    N, n, m = src.shape[0], src.shape[1], tgt.shape[1]
+    dev = src.device
+    packed = torch.empty(lib.dicp_nn_packed_bytes(N, m, 4), dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(lib.dicp_nn_workspace_bytes(N, n, m, 4), 256), dtype=torch.uint8, device=dev)
+    idx = torch.empty((N, n), dtype=torch.int32, device=dev)
+    st = _lib.stream_ptr(dev)
+    _lib.check(lib.dicp_nn_pack_f32(_lib.ptr(tgt), N, m, 6, _lib.ptr(packed), st), "pack")
+
+    def launch():
+        _lib.check(lib.dicp_nn_scan_f32(_lib.ptr(src), _lib.ptr(packed), N, n, m, _lib.ptr(idx), None, _lib.ptr(ws), ws.numel(), st), "scan")
+
+    sec = time_kernel(launch, reps=5)
+    flop = 8.0 * N * n * m                   # 3 sub, 3 mul, 2 add per (query, target) evaluation
+    peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    ach = flop / sec / 1e12
+    return {"kernel": "nn_scan_kernel<float,4>", "bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "traffic": None, "ms_per_launch": sec * 1e3,
+            "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],
+            "flop_per_pair_eval": 8, "units_per_launch": float(N) * n * m}, idx
+
+
+def roofline_gn(src, tgt, idx, pk):
+    """GN accumulate kernel alone (dicp_gn_accumulate_f32), CUDA events on the launch stream."""
+    from dicp_b200 import _functions, _lib
+    lib = _lib.load_library()
+    N, n, m = src.shape[0], src.shape[1], tgt.shape[1]
+    dev = src.device
+    p = _functions.make_params("pt2pl", 3, True, LOSS["name"], LOSS["metric"], TRIM, 5.0, 1e-12, ITERS, True, 0.0)
+    C_r = torch.cat((torch.eye(3, dtype=torch.float64).reshape(1, 9).repeat(N, 1), torch.zeros((N, 3), dtype=torch.float64)), 1).to(dev)
+    red = torch.empty((N, 32), dtype=torch.float64, device=dev)
+    w = torch.ones((N, n), dtype=torch.float32, device=dev)
+    wout = torch.empty((N, n), dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.dicp_icp_workspace_bytes(N, n, m, 4), dtype=torch.uint8, device=dev)
+    st = _lib.stream_ptr(dev)
+
+    def launch():
+        _lib.check(lib.dicp_gn_accumulate_f32(_lib.ptr(src), _lib.ptr(tgt), _lib.ptr(w), _lib.ptr(idx), _lib.ptr(C_r), N, n, m, 6,
+                                              ctypes.byref(p), _lib.ptr(wout), _lib.ptr(red), _lib.ptr(ws), ws.numel(), st), "gn")
+
+    sec = time_kernel(launch, reps=10)
+    nbytes = 48.0 * N * n                    # p 12 + gathered (q,n) 24 + idx 4 + w_init 4 + weights write 4
+    ach = nbytes / sec / 1e9
+    return {"kernel": "gn_accum_kernel<float,pt2pl,3> (+2 tiny launches)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"],
+            "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "ms_per_launch": sec * 1e3,
+            "peak_source": pk["source"], "bytes_per_correspondence": 48, "units_per_launch": float(N) * n}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from dICP.ICP import ICP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    src_h, tgt_h = make_batch(PAIRS_PER_GPU, rank * PAIRS_PER_GPU)
+    src_h, tgt_h = src_h.pin_memory(), tgt_h.pin_memory()
+    T0_h = torch.eye(4).repeat(PAIRS_PER_GPU, 1, 1).pin_memory()
+    icp = ICP(icp_type="pt2pl", differentiable=True, max_iterations=ITERS, tolerance=1e-12)
+    icp.const_iter = True
+    icp.device = dev
+    theta = torch.arange(1, 13, dtype=torch.float32, device=dev).requires_grad_(True)
+
+    src_d = src_h.to(dev).requires_grad_(True)
+    tgt_d = tgt_h.to(dev).requires_grad_(True)
+    T0_d = T0_h.to(dev)
+
+    def allreduce(vec):
+        if world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        return vec
+
+    def step_resident():
+        """inputs already in HBM; forward + backward; learning-mode all-reduce of [loss, dloss/dtheta]."""
+        src_d.grad = tgt_d.grad = theta.grad = None
+        res = icp.icp(src_d, tgt_d, T0_d, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        loss = learning_loss(res, theta)
+        loss.backward()
+        return allreduce(torch.cat((loss.detach().reshape(1), theta.grad)))
+
+    theta_h = torch.arange(1, 13, dtype=torch.float32).requires_grad_(True)
+
+    def step_e2e():
+        """public API with pinned HOST buffers: H2D of the clouds + D2H of T, loss, dloss/dtheta every step."""
+        theta_h.grad = None
+        s = src_h.to(dev, non_blocking=True).requires_grad_(True)
+        t = tgt_h.to(dev, non_blocking=True).requires_grad_(True)
+        T0 = T0_h.to(dev, non_blocking=True)
+        res = icp.icp(s, t, T0, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        th = theta_h.to(dev)
+        loss = learning_loss(res, th)
+        loss.backward()
+        out = allreduce(torch.cat((loss.detach().reshape(1), theta_h.grad.to(dev))))
+        return out.cpu(), res["T"].detach().cpu()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) * 1e-3, clocks
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    sec, clocks = timed(step_resident, args.steps, args.warmup, sampler)
+    sec_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+    steps_e2e = max(2, args.steps // 2)
+    pairs_total = PAIRS_PER_GPU * world
+
+    line = None
+    if rank == 0:
+        roof, idx = roofline_nn(src_d.detach(), tgt_d.detach(), pk)
+        roof_gn = roofline_gn(src_d.detach(), tgt_d.detach(), idx, pk)
+        cpu = None
+        if world == 1 or True:
+            cores = os.cpu_count()
+            torch.set_num_threads(cores)
+            s1, t1 = src_h[:1].clone(), tgt_h[:1].clone()
+            cpu_step(s1, t1)                        # warm-up (thread pool, allocator)
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                cpu_step(s1, t1)
+            cdt = time.perf_counter() - t0
+            cpu = {"value": reps / cdt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                   "sample": "%d x 1 pair of the C3 workload (fwd+bwd, 10 it), oracle port of the reference torch-CPU path, "
+                             "%d threads, %.1f s" % (reps, torch.get_num_threads(), cdt)}
+        # kernels of libdicp_b200.so per step: forward init+pack+10x(nn,gn,update)+finalize = 33, backward seed+10x(pair,points)+finish = 22
+        launches_per_step = (2 + 3 * ITERS + 1) + (1 + 2 * ITERS + 1)
+        h2d = src_h.numel() * 4 + tgt_h.numel() * 4 + T0_h.numel() * 4 + 12 * 4
+        d2h = 13 * 4 + PAIRS_PER_GPU * 16 * 4
+        line = {
+            "metric": METRIC, "value": pairs_total * args.steps / sec, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_total": pairs_total, "l2": "inputs larger than L2 (source+target %.0f MB per GPU, "
+                       "plus 168 MB of saved correspondences written and re-read per step)" % ((src_h.numel() + tgt_h.numel()) * 4 / 1e6),
+                       "learning_mode_allreduce": "13 floats per step over NCCL" if world > 1 else "single GPU: no collective"},
+            "clocks": clocks,
+            "e2e": {"value": pairs_total * steps_e2e / sec_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * sec_e2e / steps_e2e, "api": "dICP.ICP.ICP.icp with pinned host tensors"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof, "roofline_gn": roof_gn, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: a CUDA device is required for --impl ours (no CPU fallback)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
