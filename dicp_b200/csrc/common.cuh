@@ -77,12 +77,15 @@ struct Ctrl {
 
 // ---- nearest neighbour (nn_kernels.cu) ------------------------------------------------
 size_t nn_workspace_bytes(int N, int n, int m, int elem_size);
-// packed targets: [N, m_pad] of (x,y,z,0) in T, m_pad = round_up(m, NN_CHUNK), sentinel rows
+// packed targets: [N, m_pad] records, m_pad = round_up(m, NN_CHUNK), sentinel rows.
+//   float : (-2x,-2y,-2z,|y|^2)  16 B, expanded-form filter scan
+//   double: (x,y,z,0)            32 B, direct-form scan
 template <typename T> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 constexpr int NN_CHUNK = 16;
 inline int nn_m_pad(int m) { return (m + NN_CHUNK - 1) / NN_CHUNK * NN_CHUNK; }
+inline size_t nn_packed_bytes(int N, int m, int elem_size) { return align_up((size_t)N * nn_m_pad(m) * 4 * elem_size); }
 
 template <typename T>
 int nn_pack_targets(const T* tgt, int N, int m, int S, typename Vec4<T>::type* packed, cudaStream_t st);

@@ -246,7 +246,7 @@ finalize_kernel(const T* __restrict__ source, int n, const double* __restrict__ 
 IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size) {
   Arena ar(ws, ws_bytes);
   IcpWorkspace w;
-  w.packed = ar.take<char>((size_t)N * nn_m_pad(m) * 4 * elem_size);
+  w.packed = ar.take<char>(nn_packed_bytes(N, m, elem_size));
   w.nn_ws_bytes = nn_search_ws_bytes(N, n, m, elem_size);
   w.nn_ws = ar.take<char>(w.nn_ws_bytes > 0 ? w.nn_ws_bytes : 1);
   w.partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * RED_N);

@@ -1,17 +1,28 @@
 // nn_kernels.cu — batched brute-force nearest neighbour (replaces cdist+argmin, nn.py:32-35).
 //
-// Layout: the targets of every pair are repacked once per call into 16-byte (x,y,z,0)
-// records, padded with far-away sentinels to a multiple of NN_CHUNK.  A CTA owns
-// THREADS*Q queries of one pair (Q queries live in the registers of each thread) and
-// streams the pair's target records through shared memory in double-buffered cp.async
-// tiles; every thread reads each record with one broadcast LDS.128 and evaluates Q
-// direct-form squared distances against it (FP32 CUDA-core work, no tensor cores: a K=3
-// distance is not a contraction).  Per chunk of NN_CHUNK records only a running minimum is
-// kept (one FMNMX per evaluation); the chunk id is recorded when the chunk minimum beats
-// the best so far, and the exact index is recovered afterwards by re-evaluating that one
-// chunk with the bit-identical instruction sequence.  First-minimum tie-break like
-// torch.argmin.  When N*n is too small to fill 148 SMs the target range is split over
-// blockIdx.z and the partial (d2, idx) results are merged in split order.
+// Layout: the targets of every pair are repacked once per call into 32-byte records (16 B fp32, 32 B fp64), padded
+// with far-away sentinels to a multiple of NN_CHUNK.  A CTA owns THREADS*Q queries of one
+// pair (Q queries live in the registers of each thread) and streams the pair's records
+// through shared memory in double-buffered cp.async tiles; every thread reads each record
+// with one broadcast LDS.128 and evaluates Q distances against it.  This is FP32 CUDA-core
+// work (a K=3 distance is not a contraction worth tensor cores).
+//
+// fp32 (nn_scan_f32_kernel): a filter-and-refine scan.  Records hold (-2y, |y|^2), so
+//   v_j = |y_j|^2 - 2 x.y_j = d_j^2 - |x|^2     costs three FFMAs (half the FMA-pipe work of the
+// direct form (x-y)^2, and the record operands are served from the operand-reuse cache, which
+// is what actually limits FP32 issue on this part: one register read per bank per cycle).
+// v_j is not exact (cancellation), so it is only a filter: per chunk of NN_CHUNK records a
+// running minimum (FMNMX3, ALU pipe), per query the best chunk, its value and the best value
+// among all *other* chunks.  If that runner-up is further away than a rigorous rounding bound
+// (nn_filter_margin), the nearest neighbour must be inside the best chunk and is found there
+// with the exact direct-form distance; otherwise the query is appended to a list that
+// nn_fallback_f32_kernel resolves exactly (one warp per query, direct form over all targets,
+// warp-shuffle lexicographic argmin).  Either way the result is the direct-form fp32 argmin
+// with torch.argmin's first-minimum tie-break.  Measured on B200: 0.04 % of queries fall back.
+// fp64 (nn_scan_kernel<double>): plain direct-form scan, used by the fp64 parity tests.
+//
+// The target range is split over blockIdx.z when that is needed to fill 148 SMs or to keep the
+// tail wave short; partial (d2, idx) results are merged in split order (earlier split wins ties).
 #include "common.cuh"
 
 namespace dicp {
@@ -24,6 +35,13 @@ template <typename T> __device__ __forceinline__ T t_min(T a, T b);
 template <> __device__ __forceinline__ float t_min<float>(float a, float b) { return fminf(a, b); }
 template <> __device__ __forceinline__ double t_min<double>(double a, double b) { return fmin(a, b); }
 
+// fp32 record (-2x, -2y, -2z, fl(|y|^2)): v = |y|^2 - 2 x.y = d^2 - |x|^2 with three FFMAs
+__device__ __forceinline__ void make_record(float x, float y, float z, float4& v) {
+  v.x = -2.0f * x; v.y = -2.0f * y; v.z = -2.0f * z;
+  v.w = (float)((double)x * x + (double)y * y + (double)z * z);
+}
+__device__ __forceinline__ void make_record(double x, double y, double z, double4& v) { v.x = x; v.y = y; v.z = z; v.w = 0.0; }
+
 template <typename T>
 __global__ void nn_pack_kernel(const T* __restrict__ tgt, int m, int m_pad, int S, typename Vec4<T>::type* __restrict__ packed) {
   const int b = blockIdx.y;
@@ -32,9 +50,9 @@ __global__ void nn_pack_kernel(const T* __restrict__ tgt, int m, int m_pad, int 
   typename Vec4<T>::type v;
   if (j < m) {
     const T* row = tgt + ((size_t)b * m + j) * S;
-    v.x = row[0]; v.y = row[1]; v.z = row[2]; v.w = T(0);
+    make_record(row[0], row[1], row[2], v);
   } else {
-    v.x = v.y = v.z = Sentinel<T>::far(); v.w = T(0);
+    make_record(Sentinel<T>::far(), Sentinel<T>::far(), Sentinel<T>::far(), v);
   }
   packed[(size_t)b * m_pad + j] = v;
 }
@@ -172,6 +190,198 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// fp32: expanded-form filter scan + exact refine + exact fallback
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+// direct-form squared distance against a packed record (y = -a/2 exactly)
+__device__ __forceinline__ float dist2_rec(float x0, float x1, float x2, const float4& a) {
+  return dist2<float>(x0, x1, x2, -0.5f * a.x, -0.5f * a.y, -0.5f * a.z);
+}
+
+constexpr int NNF_THREADS = 128;
+constexpr int NNF_TILE = 512;     // records per shared-memory stage (8 KB)
+
+// Bound on |v_j - (d_j^2 - |x|^2)| for every target whose norm is at most r, plus the rounding of
+// the direct-form distance it is compared with: h carries u|y|^2, the three
+// FMAs u(|y|^2 + 2|x||y|) each; the constants are inflated for the roundings of this bound itself.
+__device__ __forceinline__ float nn_filter_margin(float xx, float v_best) {
+  const float U = 5.9604645e-8f;                                   // 2^-24
+  const float xn = sqrtf(xx);
+  const float d2 = fmaxf(v_best + xx, 0.0f);
+  const float r = xn + 2.0f * sqrtf(d2) + 1.0e-3f * xn + 1.0e-30f;   // |y| <= |x| + 2 d_best covers every target that can win
+  return 3.0f * U * (4.0f * r * r + 6.0f * xn * r) + 16.0f * U * d2;
+}
+
+template <int Q>
+__global__ void __launch_bounds__(NNF_THREADS, 1)
+nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n,
+                   int m_pad, int tiles_per_split, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
+                   float* __restrict__ part_d2, int32_t* __restrict__ part_idx, unsigned int* __restrict__ fb_count,
+                   long long* __restrict__ fb_list, const int* __restrict__ stop_flag) {
+  if (stop_flag != nullptr && *stop_flag != 0) return;
+  __shared__ __align__(16) float4 tile[2][NNF_TILE];
+  const float INF = Sentinel<float>::inf();
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int split = blockIdx.z;
+  const int N = gridDim.y;
+  const float4* tg = packed + (size_t)b * m_pad;
+
+  float C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, r[3] = {0, 0, 0};
+  if (state != nullptr) {
+    const double* rec = state + (size_t)b * ST_STRIDE;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) C[i] = (float)rec[ST_C + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r[i] = (float)rec[ST_R + i];
+  }
+  float x[Q][3], best[Q], second[Q];
+  int bchunk[Q];
+  const int q0 = blockIdx.x * (NNF_THREADS * Q) + tid;
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    int i = q0 + k * NNF_THREADS;
+    if (i >= n) i = n - 1;
+    const float* p = q + ((size_t)b * n + i) * 3;
+    float pv[3] = {p[0], p[1], p[2]};
+    if (state != nullptr) {
+      float a[3];
+      rotate(C, pv, a);                                               // ICP.py:137
+      x[k][0] = a[0] + r[0]; x[k][1] = a[1] + r[1]; x[k][2] = a[2] + r[2];
+    } else {
+      x[k][0] = pv[0]; x[k][1] = pv[1]; x[k][2] = pv[2];
+    }
+    best[k] = INF; second[k] = INF; bchunk[k] = 0;
+  }
+
+  const int tiles_total = (m_pad + NNF_TILE - 1) / NNF_TILE;
+  const int t_begin = split * tiles_per_split;
+  const int t_end = min(t_begin + tiles_per_split, tiles_total);
+
+  auto issue_tile = [&](int t, int buf) {
+    const int start = t * NNF_TILE;
+    const int cnt = min(NNF_TILE, m_pad - start);
+    for (int u = tid; u < cnt; u += NNF_THREADS) cp_async16(&tile[buf][u], tg + start + u);
+    cp_async_commit();
+  };
+
+  if (t_begin < t_end) issue_tile(t_begin, 0);
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    if (t + 1 < t_end) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int start = t * NNF_TILE;
+    const int nchunks = min(NNF_TILE, m_pad - start) / NN_CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+      float cm[Q];
+#pragma unroll
+      for (int k = 0; k < Q; ++k) cm[k] = INF;
+      const float4* ch = &tile[buf][c * NN_CHUNK];
+#pragma unroll
+      for (int j = 0; j < NN_CHUNK; j += 2) {
+        // one broadcast LDS.128 per record; the record's components sit in the same operand slot of
+        // Q consecutive FFMAs, so they are served from the operand-reuse cache, not the register file
+        const float4 a0 = ch[j], a1 = ch[j + 1];
+        float v0[Q], v1[Q];
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][2], a0.z, a0.w);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][2], a1.z, a1.w);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][1], a0.y, v0[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][1], a1.y, v1[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][0], a0.x, v0[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][0], a1.x, v1[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) cm[k] = min3(cm[k], v0[k], v1[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        second[k] = fminf(second[k], fmaxf(cm[k], best[k]));     // smallest minimum among the chunks that are not the best
+        if (cm[k] < best[k]) { best[k] = cm[k]; bchunk[k] = start / NN_CHUNK + c; }
+      }
+    }
+    __syncthreads();
+  }
+
+  // refine: exact direct-form argmin inside the winning chunk; queries whose runner-up chunk is
+  // within the error margin go to the exact fallback scan
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    const int i = q0 + k * NNF_THREADS;
+    if (i >= n) continue;
+    const size_t o = (size_t)b * n + i;
+    int found = 0;
+    float bd = INF;
+    if (t_begin < t_end) {
+      const float xx = x[k][0] * x[k][0] + x[k][1] * x[k][1] + x[k][2] * x[k][2];
+      if (!(second[k] - best[k] > nn_filter_margin(xx, best[k]))) fb_list[atomicAdd(fb_count, 1u)] = (long long)o;
+      const float4* ch = tg + (size_t)bchunk[k] * NN_CHUNK;
+#pragma unroll 4
+      for (int j = 0; j < NN_CHUNK; ++j) {
+        const float d = dist2_rec(x[k][0], x[k][1], x[k][2], ch[j]);
+        if (d < bd) { bd = d; found = bchunk[k] * NN_CHUNK + j; }
+      }
+    }
+    if (part_d2 == nullptr) {
+      idx_out[o] = found;
+      if (d2_out != nullptr) d2_out[o] = bd;
+    } else {
+      part_d2[((size_t)split * N) * n + o] = bd;
+      part_idx[((size_t)split * N) * n + o] = found;
+    }
+  }
+}
+
+// exact fallback: one warp per flagged query, lanes stride over all targets with the direct form,
+// lexicographic (d2, index) warp-shuffle argmin => first minimum
+__global__ void __launch_bounds__(256)
+nn_fallback_f32_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n,
+                       int m_pad, const unsigned int* __restrict__ fb_count, const long long* __restrict__ fb_list,
+                       int32_t* __restrict__ idx_out, float* __restrict__ d2_out, const int* __restrict__ stop_flag) {
+  if (stop_flag != nullptr && *stop_flag != 0) return;
+  const unsigned int count = *fb_count;
+  const int lane = threadIdx.x & 31;
+  const unsigned int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (unsigned int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += warps_total) {
+    const long long o = fb_list[w];
+    const int b = (int)(o / n);
+    const float* p = q + (size_t)o * 3;
+    float x0 = p[0], x1 = p[1], x2 = p[2];
+    if (state != nullptr) {
+      const double* rec = state + (size_t)b * ST_STRIDE;
+      float C[9], pv[3] = {x0, x1, x2}, a[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) C[i] = (float)rec[ST_C + i];
+      rotate(C, pv, a);
+      x0 = a[0] + (float)rec[ST_R]; x1 = a[1] + (float)rec[ST_R + 1]; x2 = a[2] + (float)rec[ST_R + 2];
+    }
+    const float4* tg = packed + (size_t)b * m_pad;
+    float bd = Sentinel<float>::inf();
+    int bi = 0x7fffffff;
+    for (int j = lane; j < m_pad; j += 32) {
+      const float d = dist2_rec(x0, x1, x2, tg[j]);
+      if (d < bd) { bd = d; bi = j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+      idx_out[o] = bi == 0x7fffffff ? 0 : bi;
+      if (d2_out != nullptr) d2_out[o] = bd;
+    }
+  }
+}
+
 template <typename T>
 __global__ void nn_merge_kernel(const T* __restrict__ part_d2, const int32_t* __restrict__ part_idx, size_t total, int nsplit,
                                 int32_t* __restrict__ idx_out, T* __restrict__ d2_out, const int* __restrict__ stop_flag) {
@@ -188,62 +398,115 @@ __global__ void nn_merge_kernel(const T* __restrict__ part_d2, const int32_t* __
   if (d2_out != nullptr) d2_out[o] = bd;
 }
 
-template <typename T> struct NNCfg;
-template <> struct NNCfg<float> { static constexpr int Q = 4; };
-template <> struct NNCfg<double> { static constexpr int Q = 2; };
+// grid: x = query blocks, y = pair, z = target split.  Split when the query grid alone cannot
+// fill the machine, and when it gives only a few waves (a short last wave costs up to one
+// CTA duration: keep CTAs short relative to the whole launch).
+struct NNPlan { int q, gx, nsplit, tiles_per_split, threads, tile; };
 
-static void nn_plan(int N, int n, int m, int Q, int& gx, int& nsplit, int& tiles_per_split) {
+static NNPlan nn_plan(int N, int n, int m, int elem_size) {
+  NNPlan p;
   const int m_pad = nn_m_pad(m);
-  gx = (n + NN_THREADS * Q - 1) / (NN_THREADS * Q);
-  const int tiles_total = (m_pad + NN_TILE - 1) / NN_TILE;
-  const long long base = (long long)gx * N;
-  const long long want = 148LL * 8;          // CTAs needed to fill the machine at 8 CTAs / SM
+  int ctas_per_sm;
+  if (elem_size == 4) {
+    // 16 queries per thread (2 CTAs / SM) once there is enough work for >= 8 waves of them, else 8 (4 CTAs / SM)
+    p.threads = NNF_THREADS; p.tile = NNF_TILE;
+    const long long ctas16 = (long long)N * ((n + NNF_THREADS * 16 - 1) / (NNF_THREADS * 16));
+    p.q = ctas16 >= 148LL * 2 * 8 ? 16 : 8;
+    ctas_per_sm = p.q == 16 ? 2 : 4;
+  } else {
+    p.threads = NN_THREADS; p.tile = NN_TILE; p.q = 2; ctas_per_sm = 4;
+  }
+  p.gx = (n + p.threads * p.q - 1) / (p.threads * p.q);
+  const int tiles_total = (m_pad + p.tile - 1) / p.tile;
+  const long long base = (long long)p.gx * N;
+  const long long slots = 148LL * ctas_per_sm;
+  const long long want = slots * 16;         // >= 16 waves => tail loss of a few percent at most
   long long s = (want + base - 1) / base;
+  const long long max_by_work = tiles_total / 8 > 0 ? tiles_total / 8 : 1;   // >= 8 tiles per CTA keeps prologue/refine overhead small
+  const long long fill = (slots + base - 1) / base;                            // but always fill the machine
+  if (s > max_by_work) s = max_by_work > fill ? max_by_work : fill;
   if (s > tiles_total) s = tiles_total;
   if (s > 64) s = 64;
   if (s < 1) s = 1;
-  tiles_per_split = (int)((tiles_total + s - 1) / s);
-  nsplit = (tiles_total + tiles_per_split - 1) / tiles_per_split;
+  p.tiles_per_split = (int)((tiles_total + s - 1) / s);
+  p.nsplit = (tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  return p;
 }
 
-size_t nn_search_ws_bytes(int N, int n, int m, int elem_size) {
-  int gx, nsplit, tps;
-  nn_plan(N, n, m, elem_size == 4 ? NNCfg<float>::Q : NNCfg<double>::Q, gx, nsplit, tps);
-  if (nsplit == 1) return 0;
-  return align_up((size_t)nsplit * N * n * elem_size) + align_up((size_t)nsplit * N * n * 4);
+// workspace of one search: [split partials d2 | split partials idx] [fallback counter] [fallback list]
+struct NNWorkspace { void* part_d2; int32_t* part_idx; unsigned int* fb_count; long long* fb_list; size_t total; };
+static NNWorkspace nn_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size) {
+  const NNPlan p = nn_plan(N, n, m, elem_size);
+  Arena ar(ws, ws_bytes);
+  NNWorkspace w;
+  w.part_d2 = nullptr; w.part_idx = nullptr; w.fb_count = nullptr; w.fb_list = nullptr;
+  if (p.nsplit > 1) {
+    w.part_d2 = ar.take<char>((size_t)p.nsplit * N * n * elem_size);
+    w.part_idx = ar.take<int32_t>((size_t)p.nsplit * N * n);
+  }
+  if (elem_size == 4) {
+    w.fb_count = ar.take<unsigned int>(1);
+    w.fb_list = ar.take<long long>((size_t)N * n * p.nsplit);     // every (query, split) can flag at most once
+  }
+  w.total = ar.off;
+  return w;
+}
+
+size_t nn_search_ws_bytes(int N, int n, int m, int elem_size) { return nn_ws_layout(nullptr, 0, N, n, m, elem_size).total; }
+
+static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_t st, const float* q, const double* state, const float4* packed,
+                       int n, int m_pad, int32_t* idx_out, float* d2_out, const int* stop_flag) {
+  dim3 grid(p.gx, N, p.nsplit);
+  DICP_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(unsigned int), st));
+  if (p.q == 16)
+    nn_scan_f32_kernel<16><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
+                                                          w.part_idx, w.fb_count, w.fb_list, stop_flag);
+  else
+    nn_scan_f32_kernel<8><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
+                                                         w.part_idx, w.fb_count, w.fb_list, stop_flag);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_t st, const double* q, const double* state, const double4* packed,
+                       int n, int m_pad, int32_t* idx_out, double* d2_out, const int* stop_flag) {
+  dim3 grid(p.gx, N, p.nsplit);
+  nn_scan_kernel<double, 2><<<grid, NN_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (double*)w.part_d2,
+                                                         w.part_idx, stop_flag);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+static int launch_fallback(const NNWorkspace& w, cudaStream_t st, const float* q, const double* state, const float4* packed, int n, int m_pad,
+                           int32_t* idx_out, float* d2_out, const int* stop_flag) {
+  nn_fallback_f32_kernel<<<148 * 4, 256, 0, st>>>(q, state, packed, n, m_pad, w.fb_count, w.fb_list, idx_out, d2_out, stop_flag);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+static int launch_fallback(const NNWorkspace&, cudaStream_t, const double*, const double*, const double4*, int, int, int32_t*, double*, const int*) {
+  return 0;   // the fp64 scan is exact (direct form)
 }
 
 template <typename T>
 int nn_search(const T* q, const double* state, const typename Vec4<T>::type* packed, int N, int n, int m,
               int32_t* idx_out, T* d2_out, const int* stop_flag, void* ws, size_t ws_bytes, cudaStream_t st) {
-  constexpr int Q = NNCfg<T>::Q;
-  int gx, nsplit, tps;
-  nn_plan(N, n, m, Q, gx, nsplit, tps);
-  const int m_pad = nn_m_pad(m);
-  T* part_d2 = nullptr;
-  int32_t* part_idx = nullptr;
-  if (nsplit > 1) {
-    Arena ar(ws, ws_bytes);
-    part_d2 = ar.take<T>((size_t)nsplit * N * n);
-    part_idx = ar.take<int32_t>((size_t)nsplit * N * n);
-    if (part_d2 == nullptr || part_idx == nullptr) { set_error("nn_search: workspace too small"); return DICP_ERR_WORKSPACE; }
-  }
   if (N > 65535) { set_error("nn_search: N > 65535 pairs per call is not supported"); return DICP_ERR_ARG; }
-  dim3 grid(gx, N, nsplit);
-  nn_scan_kernel<T, Q><<<grid, NN_THREADS, 0, st>>>(q, state, packed, n, m_pad, tps, idx_out, d2_out, part_d2, part_idx, stop_flag);
-  DICP_LAUNCH_CHECK();
-  if (nsplit > 1) {
+  const NNPlan p = nn_plan(N, n, m, sizeof(T));
+  const int m_pad = nn_m_pad(m);
+  const NNWorkspace w = nn_ws_layout(ws, ws_bytes, N, n, m, sizeof(T));
+  if (w.total > 0 && (ws == nullptr || w.total > ws_bytes)) { set_error("nn_search: workspace too small"); return DICP_ERR_WORKSPACE; }
+  int rc = launch_scan(p, w, N, st, q, state, packed, n, m_pad, idx_out, d2_out, stop_flag);
+  if (rc) return rc;
+  if (p.nsplit > 1) {
     const size_t total = (size_t)N * n;
-    nn_merge_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part_d2, part_idx, total, nsplit, idx_out, d2_out, stop_flag);
+    nn_merge_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)w.part_d2, w.part_idx, total, p.nsplit, idx_out, d2_out, stop_flag);
     DICP_LAUNCH_CHECK();
   }
-  return 0;
+  return launch_fallback(w, st, q, state, packed, n, m_pad, idx_out, d2_out, stop_flag);
 }
 template int nn_search<float>(const float*, const double*, const float4*, int, int, int, int32_t*, float*, const int*, void*, size_t, cudaStream_t);
 template int nn_search<double>(const double*, const double*, const double4*, int, int, int, int32_t*, double*, const int*, void*, size_t, cudaStream_t);
 
 size_t nn_workspace_bytes(int N, int n, int m, int elem_size) {
-  return align_up((size_t)N * nn_m_pad(m) * 4 * elem_size) + nn_search_ws_bytes(N, n, m, elem_size);
+  return nn_packed_bytes(N, m, elem_size) + nn_search_ws_bytes(N, n, m, elem_size);
 }
 
 template <typename T>
@@ -303,7 +566,7 @@ int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, 
                        void* ws, size_t ws_bytes, void* stream) {
   return dicp::nn_argmin_impl<double>(q, tgt, N, n, m, S, idx_out, d2_out, ws, ws_bytes, stream);
 }
-size_t dicp_nn_packed_bytes(int N, int m, int elem_size) { return dicp::align_up((size_t)N * dicp::nn_m_pad(m) * 4 * elem_size); }
+size_t dicp_nn_packed_bytes(int N, int m, int elem_size) { return dicp::nn_packed_bytes(N, m, elem_size); }
 int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream) {
   DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
   return dicp::nn_pack_targets<float>(tgt, N, m, S, (float4*)packed, (cudaStream_t)stream);

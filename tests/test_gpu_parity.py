@@ -190,6 +190,18 @@ def test_nn_random_clouds(shape, dtype):
     _nn_check(x, y)
 
 
+@pytest.mark.parametrize("offset,extent", [(1000.0, 20.0), (30000.0, 5.0), (0.0, 2000.0)])
+def test_nn_far_from_origin_uses_exact_fallback(offset, extent):
+    """Clouds far from the origin make the fp32 expanded-form filter ambiguous for many queries
+    (cancellation ~ eps * |x|^2); those must be resolved by the exact fallback scan, so the
+    indices still equal the fp64-exact argmin on tie-free queries."""
+    gen = torch.Generator().manual_seed(int(offset) + 5)
+    N, n, m = 2, 3000, 5000
+    y = (torch.rand((N, m, 3), generator=gen, dtype=torch.float64) * 2 - 1) * extent + offset
+    x = y[:, torch.randperm(m, generator=gen)[:n]] + 0.01 * extent / 20 * torch.randn((N, n, 3), generator=gen, dtype=torch.float64)
+    _nn_check(x.float(), y.float(), min_ok=0.95)
+
+
 def test_nn_first_minimum_on_exact_ties():
     """duplicated targets: torch.argmin returns the first (nn.py:35)."""
     from dicp_b200._functions import nn_argmin

@@ -1,0 +1,585 @@
+// nn_tune.cu — standalone tuning harness for the fp32 packed-math NN scan (not part of the
+// library).  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o nn_tune nn_tune.cu
+// Runs several structural variants of the scan on N pairs x n x n points and prints ms and
+// the fraction of the FP32 peak (8 FLOP per evaluation).  All variants must produce the same
+// indices as variant 0.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+typedef unsigned long long u64;
+#ifdef VOLATILE_ASM
+#define VOL volatile
+#else
+#define VOL
+#endif
+struct __align__(16) RecF32 { float nx0, nx1, ny0, ny1, nz0, nz1, pad0, pad1; };
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm VOL("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm VOL("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm VOL("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float min3(float a, float b, float c) { float r; asm VOL("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ float dist2_rec(float x0, float x1, float x2, float nx, float ny, float nz) {
+  const float dx = __fadd_rn(x0, nx), dy = __fadd_rn(x1, ny), dz = __fadd_rn(x2, nz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+constexpr int CHUNK = 16;
+
+// VAR 0: per j-pair, loop over query pairs (adds, chain, min) — the first packed version
+// VAR 1: per j-pair, stage-wise over all query pairs (all adds, all muls, all fmas, all mins)
+// VAR 2: like 1 but per j-quad (4 targets at once; min3 twice)
+// SMEMID: keep the winning chunk id in shared memory (predicated STS) instead of a register
+template <int Q, int THREADS, int MINB, int TILE, int VAR, bool SMEMID, int ABL = 0>
+__global__ void __launch_bounds__(THREADS, MINB)
+scan_kernel(const float* __restrict__ q, const RecF32* __restrict__ packed, int n, int m_pad, int32_t* __restrict__ idx_out) {
+  __shared__ __align__(16) RecF32 tile[2][TILE];
+  __shared__ unsigned short chunk_id[SMEMID ? Q : 1][SMEMID ? THREADS : 1];
+  constexpr int QP = Q / 2;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const RecF32* tg = packed + (size_t)b * m_pad;
+  float x[Q][3], best[Q];
+  int bchunk[SMEMID ? 1 : Q];
+  const int q0 = blockIdx.x * (THREADS * Q) + tid;
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    int i = q0 + k * THREADS;
+    if (i >= n) i = n - 1;
+    const float* p = q + ((size_t)b * n + i) * 3;
+    x[k][0] = p[0]; x[k][1] = p[1]; x[k][2] = p[2];
+    best[k] = __int_as_float(0x7f800000);
+    if (!SMEMID) bchunk[k] = 0; else chunk_id[k][tid] = 0;
+  }
+  u64 X[QP], Y[QP], Z[QP];
+#pragma unroll
+  for (int k = 0; k < QP; ++k) {
+    X[k] = pack2(x[2 * k][0], x[2 * k + 1][0]);
+    Y[k] = pack2(x[2 * k][1], x[2 * k + 1][1]);
+    Z[k] = pack2(x[2 * k][2], x[2 * k + 1][2]);
+  }
+  const int tiles_total = (m_pad + TILE - 1) / TILE;
+  auto issue_tile = [&](int t, int buf) {
+    const int start = t * TILE;
+    const int cnt = min(TILE, m_pad - start);
+    const char* src = (const char*)(tg + start);
+    char* dst = (char*)&tile[buf][0];
+    for (int u = tid; u < cnt * 2; u += THREADS) cp_async16(dst + (size_t)u * 16, src + (size_t)u * 16);
+    cp_async_commit();
+  };
+  issue_tile(0, 0);
+  for (int t = 0; t < tiles_total; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < tiles_total) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int start = t * TILE;
+    const int nchunks = min(TILE, m_pad - start) / CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+      float cm[Q];
+#pragma unroll
+      for (int k = 0; k < Q; ++k) cm[k] = __int_as_float(0x7f800000);
+      const RecF32* ch = &tile[buf][c * CHUNK];
+      if (VAR == 0) {
+        ulonglong2 h0, h1; u64 hz0, hz1;
+        if (ABL & 1) {
+          h0 = *reinterpret_cast<const ulonglong2*>(&tile[buf][0].nx0); hz0 = *reinterpret_cast<const u64*>(&tile[buf][0].nz0);
+          h1 = *reinterpret_cast<const ulonglong2*>(&tile[buf][1].nx0); hz1 = *reinterpret_cast<const u64*>(&tile[buf][1].nz0);
+        }
+#pragma unroll
+        for (int j = 0; j < CHUNK; j += 2) {
+          ulonglong2 a0, a1; u64 z0, z1;
+          if (ABL & 1) { a0 = h0; a1 = h1; z0 = hz0 + j; z1 = hz1 + c; }
+          else {
+            a0 = *reinterpret_cast<const ulonglong2*>(&ch[j].nx0);
+            z0 = *reinterpret_cast<const u64*>(&ch[j].nz0);
+            a1 = *reinterpret_cast<const ulonglong2*>(&ch[j + 1].nx0);
+            z1 = *reinterpret_cast<const u64*>(&ch[j + 1].nz0);
+          }
+#pragma unroll
+          for (int k = 0; k < QP; ++k) {
+            const u64 dx0 = add2(X[k], a0.x), dy0 = add2(Y[k], a0.y), dz0 = add2(Z[k], z0);
+            const u64 dx1 = add2(X[k], a1.x), dy1 = add2(Y[k], a1.y), dz1 = add2(Z[k], z1);
+            const u64 d0 = fma2(dz0, dz0, fma2(dy0, dy0, mul2(dx0, dx0)));
+            const u64 d1 = fma2(dz1, dz1, fma2(dy1, dy1, mul2(dx1, dx1)));
+            float l0, h0, l1, h1;
+            unpack2(d0, l0, h0); unpack2(d1, l1, h1);
+            cm[2 * k] = min3(cm[2 * k], l0, l1);
+            if (ABL & 2) cm[2 * k + 1] = __int_as_float(__float_as_int(cm[2 * k + 1]) ^ __float_as_int(h0) ^ __float_as_int(h1));
+            else cm[2 * k + 1] = min3(cm[2 * k + 1], h0, h1);
+          }
+        }
+      } else if (VAR == 1) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; j += 2) {
+          const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(&ch[j].nx0);
+          const u64 z0 = *reinterpret_cast<const u64*>(&ch[j].nz0);
+          const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(&ch[j + 1].nx0);
+          const u64 z1 = *reinterpret_cast<const u64*>(&ch[j + 1].nz0);
+          u64 d0[QP], d1[QP], e0[QP], e1[QP], f0[QP], f1[QP];
+#pragma unroll
+          for (int k = 0; k < QP; ++k) { d0[k] = add2(X[k], a0.x); d1[k] = add2(X[k], a1.x); }
+#pragma unroll
+          for (int k = 0; k < QP; ++k) { e0[k] = add2(Y[k], a0.y); e1[k] = add2(Y[k], a1.y); }
+#pragma unroll
+          for (int k = 0; k < QP; ++k) { d0[k] = mul2(d0[k], d0[k]); d1[k] = mul2(d1[k], d1[k]); }
+#pragma unroll
+          for (int k = 0; k < QP; ++k) { f0[k] = add2(Z[k], z0); f1[k] = add2(Z[k], z1); }
+#pragma unroll
+          for (int k = 0; k < QP; ++k) { d0[k] = fma2(e0[k], e0[k], d0[k]); d1[k] = fma2(e1[k], e1[k], d1[k]); }
+#pragma unroll
+          for (int k = 0; k < QP; ++k) { d0[k] = fma2(f0[k], f0[k], d0[k]); d1[k] = fma2(f1[k], f1[k], d1[k]); }
+#pragma unroll
+          for (int k = 0; k < QP; ++k) {
+            float l0, h0, l1, h1;
+            unpack2(d0[k], l0, h0); unpack2(d1[k], l1, h1);
+            cm[2 * k] = min3(cm[2 * k], l0, l1);
+            cm[2 * k + 1] = min3(cm[2 * k + 1], h0, h1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CHUNK; j += 4) {
+          ulonglong2 a[4]; u64 z[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { a[g] = *reinterpret_cast<const ulonglong2*>(&ch[j + g].nx0); z[g] = *reinterpret_cast<const u64*>(&ch[j + g].nz0); }
+          u64 d[4][QP], e[4][QP];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int k = 0; k < QP; ++k) d[g][k] = add2(X[k], a[g].x);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int k = 0; k < QP; ++k) { e[g][k] = add2(Y[k], a[g].y); d[g][k] = mul2(d[g][k], d[g][k]); }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int k = 0; k < QP; ++k) { d[g][k] = fma2(e[g][k], e[g][k], d[g][k]); e[g][k] = add2(Z[k], z[g]); }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int k = 0; k < QP; ++k) d[g][k] = fma2(e[g][k], e[g][k], d[g][k]);
+#pragma unroll
+          for (int k = 0; k < QP; ++k) {
+            float l0, h0, l1, h1, l2, h2, l3, h3;
+            unpack2(d[0][k], l0, h0); unpack2(d[1][k], l1, h1); unpack2(d[2][k], l2, h2); unpack2(d[3][k], l3, h3);
+            cm[2 * k] = min3(min3(cm[2 * k], l0, l1), l2, l3);
+            cm[2 * k + 1] = min3(min3(cm[2 * k + 1], h0, h1), h2, h3);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        if (ABL & 4) { best[k] = fminf(best[k], cm[k]); continue; }
+        if (cm[k] < best[k]) {
+          best[k] = cm[k];
+          if (SMEMID) chunk_id[k][tid] = (unsigned short)(start / CHUNK + c); else bchunk[k] = start / CHUNK + c;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    const int i = q0 + k * THREADS;
+    if (i >= n) continue;
+    const int bc = SMEMID ? (int)chunk_id[k][tid] : bchunk[k];
+    int found = -1;
+    const RecF32* ch = tg + (size_t)bc * CHUNK;
+    for (int j = 0; j < CHUNK; ++j) {
+      const float d = dist2_rec(x[k][0], x[k][1], x[k][2], ch[j].nx0, ch[j].ny0, ch[j].nz0);
+      if (found < 0 && d == best[k]) found = bc * CHUNK + j;
+    }
+    idx_out[(size_t)b * n + i] = found < 0 ? 0 : found;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// expanded form: v_j = |y_j|^2 - 2 x.y_j  (= d^2 - |x|^2), 3 FFMA2 per 2 evaluations, filter + refine
+// record: (-2x,-2x,-2y,-2y,-2z,-2z,h,h), h = fl(|y|^2)
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) RecE { float ax0, ax1, ay0, ay1, az0, az1, h0, h1; };
+__global__ void pack_kernel_e(const float* tgt, int m, RecE* packed) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const float* r = tgt + ((size_t)b * m + j) * 3;
+  const double h = (double)r[0] * r[0] + (double)r[1] * r[1] + (double)r[2] * r[2];
+  RecE v;
+  v.ax0 = v.ax1 = -2.f * r[0]; v.ay0 = v.ay1 = -2.f * r[1]; v.az0 = v.az1 = -2.f * r[2]; v.h0 = v.h1 = (float)h;
+  packed[(size_t)b * m + j] = v;
+}
+// ORDER 0: per target pair, k inner;  ORDER 1: stage-wise over k (same target operand in consecutive instructions)
+template <int Q, int THREADS, int MINB, int TILE, int ORDER>
+__global__ void __launch_bounds__(THREADS, MINB)
+scan_expanded(const float* __restrict__ q, const RecE* __restrict__ packed, int n, int m_pad, int32_t* __restrict__ idx_out,
+              unsigned int* __restrict__ nflag) {
+  __shared__ __align__(16) RecE tile[2][TILE];
+  constexpr int QP = Q / 2;
+  const float INF = __int_as_float(0x7f800000);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const RecE* tg = packed + (size_t)b * m_pad;
+  float x[Q][3], best[Q], second[Q];
+  int bchunk[Q];
+  const int q0 = blockIdx.x * (THREADS * Q) + tid;
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    int i = q0 + k * THREADS;
+    if (i >= n) i = n - 1;
+    const float* p = q + ((size_t)b * n + i) * 3;
+    x[k][0] = p[0]; x[k][1] = p[1]; x[k][2] = p[2];
+    best[k] = INF; second[k] = INF; bchunk[k] = 0;
+  }
+  u64 X[QP], Y[QP], Z[QP];
+#pragma unroll
+  for (int k = 0; k < QP; ++k) {
+    X[k] = pack2(x[2 * k][0], x[2 * k + 1][0]);
+    Y[k] = pack2(x[2 * k][1], x[2 * k + 1][1]);
+    Z[k] = pack2(x[2 * k][2], x[2 * k + 1][2]);
+  }
+  const int tiles_total = (m_pad + TILE - 1) / TILE;
+  auto issue_tile = [&](int t, int buf) {
+    const int start = t * TILE;
+    const int cnt = min(TILE, m_pad - start);
+    const char* src = (const char*)(tg + start);
+    char* dst = (char*)&tile[buf][0];
+    for (int u = tid; u < cnt * 2; u += THREADS) cp_async16(dst + (size_t)u * 16, src + (size_t)u * 16);
+    cp_async_commit();
+  };
+  issue_tile(0, 0);
+  for (int t = 0; t < tiles_total; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < tiles_total) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int start = t * TILE;
+    const int nchunks = min(TILE, m_pad - start) / CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+      float cm[Q];
+#pragma unroll
+      for (int k = 0; k < Q; ++k) cm[k] = INF;
+      const RecE* ch = &tile[buf][c * CHUNK];
+#pragma unroll
+      for (int j = 0; j < CHUNK; j += 2) {
+        const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(&ch[j].ax0);
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(&ch[j].az0);
+        const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(&ch[j + 1].ax0);
+        const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(&ch[j + 1].az0);
+        if (ORDER == 0) {
+#pragma unroll
+          for (int k = 0; k < QP; ++k) {
+            const u64 d0 = fma2(X[k], a0.x, fma2(Y[k], a0.y, fma2(Z[k], b0.x, b0.y)));
+            const u64 d1 = fma2(X[k], a1.x, fma2(Y[k], a1.y, fma2(Z[k], b1.x, b1.y)));
+            float l0, h0, l1, h1;
+            unpack2(d0, l0, h0); unpack2(d1, l1, h1);
+            cm[2 * k] = min3(cm[2 * k], l0, l1);
+            cm[2 * k + 1] = min3(cm[2 * k + 1], h0, h1);
+          }
+        } else {
+          u64 d0[QP], d1[QP];
+#pragma unroll
+          for (int k = 0; k < QP; ++k) d0[k] = fma2(Z[k], b0.x, b0.y);
+#pragma unroll
+          for (int k = 0; k < QP; ++k) d1[k] = fma2(Z[k], b1.x, b1.y);
+#pragma unroll
+          for (int k = 0; k < QP; ++k) d0[k] = fma2(Y[k], a0.y, d0[k]);
+#pragma unroll
+          for (int k = 0; k < QP; ++k) d1[k] = fma2(Y[k], a1.y, d1[k]);
+#pragma unroll
+          for (int k = 0; k < QP; ++k) d0[k] = fma2(X[k], a0.x, d0[k]);
+#pragma unroll
+          for (int k = 0; k < QP; ++k) d1[k] = fma2(X[k], a1.x, d1[k]);
+#pragma unroll
+          for (int k = 0; k < QP; ++k) {
+            float l0, h0, l1, h1;
+            unpack2(d0[k], l0, h0); unpack2(d1[k], l1, h1);
+            cm[2 * k] = min3(cm[2 * k], l0, l1);
+            cm[2 * k + 1] = min3(cm[2 * k + 1], h0, h1);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        second[k] = fminf(second[k], fmaxf(cm[k], best[k]));     // smallest chunk minimum among the chunks that are not the best one
+        if (cm[k] < best[k]) { best[k] = cm[k]; bchunk[k] = start / CHUNK + c; }
+      }
+    }
+    __syncthreads();
+  }
+  const float U = 5.9604645e-8f;   // 2^-24
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    const int i = q0 + k * THREADS;
+    if (i >= n) continue;
+    const float xx = x[k][0] * x[k][0] + x[k][1] * x[k][1] + x[k][2] * x[k][2];
+    const float d2b = fmaxf(best[k] + xx, 0.f);
+    const float r = sqrtf(xx) + sqrtf(d2b) * 1.0001f + 1e-30f;   // |y| <= |x| + d for the candidates that matter
+    const float E = 14.0f * U * (sqrtf(xx) + r) * (sqrtf(xx) + r);
+    const bool ambiguous = !(second[k] - best[k] > 2.0f * E);
+    if (ambiguous) atomicAdd(nflag, 1u);
+    int found = -1; float bd = INF;
+    const RecE* ch = tg + (size_t)bchunk[k] * CHUNK;
+    for (int j = 0; j < CHUNK; ++j) {
+      const float d = dist2_rec(x[k][0], x[k][1], x[k][2], 0.5f * ch[j].ax0, 0.5f * ch[j].ay0, 0.5f * ch[j].az0);
+      if (d < bd) { bd = d; found = bchunk[k] * CHUNK + j; }
+    }
+    idx_out[(size_t)b * n + i] = found < 0 ? 0 : found;
+  }
+}
+
+template <int Q, int THREADS, int MINB, int TILE, int ORDER>
+void run_e(const char* name);
+
+// scalar expanded form: record (ax,ay,az,h) 16 B, 3 FFMA + min per evaluation; target operand reused across k
+__global__ void pack_kernel_s(const float* tgt, int m, float4* packed) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const float* r = tgt + ((size_t)b * m + j) * 3;
+  const double h = (double)r[0] * r[0] + (double)r[1] * r[1] + (double)r[2] * r[2];
+  packed[(size_t)b * m + j] = make_float4(-2.f * r[0], -2.f * r[1], -2.f * r[2], (float)h);
+}
+template <int Q, int THREADS, int MINB, int TILE, int MINMODE>
+__global__ void __launch_bounds__(THREADS, MINB)
+scan_scalar_e(const float* __restrict__ q, const float4* __restrict__ packed, int n, int m_pad, int32_t* __restrict__ idx_out,
+              unsigned int* __restrict__ nflag) {
+  __shared__ __align__(16) float4 tile[2][TILE];
+  const float INF = __int_as_float(0x7f800000);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const float4* tg = packed + (size_t)b * m_pad;
+  float x[Q][3], best[Q], second[Q];
+  int bchunk[Q];
+  const int q0 = blockIdx.x * (THREADS * Q) + tid;
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    int i = q0 + k * THREADS;
+    if (i >= n) i = n - 1;
+    const float* p = q + ((size_t)b * n + i) * 3;
+    x[k][0] = p[0]; x[k][1] = p[1]; x[k][2] = p[2];
+    best[k] = INF; second[k] = INF; bchunk[k] = 0;
+  }
+  const int tiles_total = (m_pad + TILE - 1) / TILE;
+  auto issue_tile = [&](int t, int buf) {
+    const int start = t * TILE;
+    const int cnt = min(TILE, m_pad - start);
+    for (int u = tid; u < cnt; u += THREADS) cp_async16(&tile[buf][u], tg + start + u);
+    cp_async_commit();
+  };
+  issue_tile(0, 0);
+  for (int t = 0; t < tiles_total; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < tiles_total) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int start = t * TILE;
+    const int nchunks = min(TILE, m_pad - start) / CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+      float cm[Q];
+#pragma unroll
+      for (int k = 0; k < Q; ++k) cm[k] = INF;
+      const float4* ch = &tile[buf][c * CHUNK];
+#pragma unroll
+      for (int j = 0; j < CHUNK; j += 2) {
+        const float4 a0 = ch[j], a1 = ch[j + 1];
+        float v0[Q], v1[Q];
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][2], a0.z, a0.w);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][2], a1.z, a1.w);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][1], a0.y, v0[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][1], a1.y, v1[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][0], a0.x, v0[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][0], a1.x, v1[k]);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+          if (MINMODE == 0) cm[k] = min3(cm[k], v0[k], v1[k]);
+          else cm[k] = fminf(fminf(cm[k], v0[k]), v1[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        second[k] = fminf(second[k], fmaxf(cm[k], best[k]));
+        if (cm[k] < best[k]) { best[k] = cm[k]; bchunk[k] = start / CHUNK + c; }
+      }
+    }
+    __syncthreads();
+  }
+  const float U = 5.9604645e-8f;
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    const int i = q0 + k * THREADS;
+    if (i >= n) continue;
+    const float xx = x[k][0] * x[k][0] + x[k][1] * x[k][1] + x[k][2] * x[k][2];
+    const float d2b = fmaxf(best[k] + xx, 0.f);
+    const float r = sqrtf(xx) + sqrtf(d2b) * 1.0001f + 1e-30f;
+    const float E = 14.0f * U * (sqrtf(xx) + r) * (sqrtf(xx) + r);
+    if (!(second[k] - best[k] > 2.0f * E)) atomicAdd(nflag, 1u);
+    int found = -1; float bd = INF;
+    const float4* ch = tg + (size_t)bchunk[k] * CHUNK;
+    for (int j = 0; j < CHUNK; ++j) {
+      const float4 a = ch[j];
+      const float d = dist2_rec(x[k][0], x[k][1], x[k][2], 0.5f * a.x, 0.5f * a.y, 0.5f * a.z);
+      if (d < bd) { bd = d; found = bchunk[k] * CHUNK + j; }
+    }
+    idx_out[(size_t)b * n + i] = found < 0 ? 0 : found;
+  }
+}
+
+__global__ void pack_kernel(const float* tgt, int m, RecF32* packed) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const float* r = tgt + ((size_t)b * m + j) * 3;
+  RecF32 v;
+  v.nx0 = v.nx1 = -r[0]; v.ny0 = v.ny1 = -r[1]; v.nz0 = v.nz1 = -r[2]; v.pad0 = v.pad1 = 0.f;
+  packed[(size_t)b * m + j] = v;
+}
+
+static int N = 64, n = 16384;
+static float *d_q, *d_t;
+static RecF32* d_p;
+static int32_t *d_idx, *d_ref;
+
+template <int Q, int THREADS, int MINB, int TILE, int VAR, bool SMEMID, int ABL = 0>
+void run(const char* name) {
+  dim3 grid((n + THREADS * Q - 1) / (THREADS * Q), N);
+  cudaFuncAttributes at;
+  cudaFuncGetAttributes(&at, scan_kernel<Q, THREADS, MINB, TILE, VAR, SMEMID, ABL>);
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_kernel<Q, THREADS, MINB, TILE, VAR, SMEMID, ABL>, THREADS, 0);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int it = 0; it < 4; ++it) {
+    cudaEventRecord(e0);
+    scan_kernel<Q, THREADS, MINB, TILE, VAR, SMEMID, ABL><<<grid, THREADS>>>(d_q, d_p, n, n, d_idx);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (it > 0 && ms < best) best = ms;
+  }
+  cudaError_t err = cudaGetLastError();
+  static bool have_ref = false;
+  long long mism = -1;
+  std::vector<int32_t> h((size_t)N * n);
+  cudaMemcpy(h.data(), d_idx, h.size() * 4, cudaMemcpyDeviceToHost);
+  if (!have_ref) { cudaMemcpy(d_ref, d_idx, h.size() * 4, cudaMemcpyDeviceToDevice); have_ref = true; mism = 0; }
+  else {
+    std::vector<int32_t> r((size_t)N * n);
+    cudaMemcpy(r.data(), d_ref, r.size() * 4, cudaMemcpyDeviceToHost);
+    mism = 0;
+    for (size_t i = 0; i < h.size(); ++i) mism += h[i] != r[i];
+  }
+  const double tf = 8.0 * N * (double)n * n / (best * 1e-3) / 1e12;
+  printf("%-44s regs=%3d occ=%2d CTA/SM  %8.3f ms  %6.2f TFLOP/s  %5.1f%% of 74.45  mismatch=%lld %s\n", name, at.numRegs, nb, best, tf,
+         100.0 * tf / 74.45, mism, err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
+
+static RecE* d_pe; static unsigned int* d_flag;
+template <int Q, int THREADS, int MINB, int TILE, int ORDER>
+void run_e(const char* name) {
+  dim3 grid((n + THREADS * Q - 1) / (THREADS * Q), N);
+  cudaFuncAttributes at;
+  cudaFuncGetAttributes(&at, scan_expanded<Q, THREADS, MINB, TILE, ORDER>);
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_expanded<Q, THREADS, MINB, TILE, ORDER>, THREADS, 0);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int it = 0; it < 4; ++it) {
+    cudaMemset(d_flag, 0, 4);
+    cudaEventRecord(e0);
+    scan_expanded<Q, THREADS, MINB, TILE, ORDER><<<grid, THREADS>>>(d_q, d_pe, n, n, d_idx, d_flag);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (it > 0 && ms < best) best = ms;
+  }
+  cudaError_t err = cudaGetLastError();
+  std::vector<int32_t> h((size_t)N * n), r((size_t)N * n);
+  cudaMemcpy(h.data(), d_idx, h.size() * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(r.data(), d_ref, r.size() * 4, cudaMemcpyDeviceToHost);
+  long long mism = 0; for (size_t i = 0; i < h.size(); ++i) mism += h[i] != r[i];
+  unsigned int nf; cudaMemcpy(&nf, d_flag, 4, cudaMemcpyDeviceToHost);
+  const double tf = 8.0 * N * (double)n * n / (best * 1e-3) / 1e12;
+  printf("%-44s regs=%3d occ=%2d CTA/SM  %8.3f ms  %6.2f TFLOP/s(8/eval)  %5.1f%%  mismatch(unfiltered)=%lld flagged=%u (%.3f%%) %s\n", name, at.numRegs, nb, best,
+         tf, 100.0 * tf / 74.45, mism, nf, 100.0 * nf / ((double)N * n), err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
+static float4* d_ps;
+template <int Q, int THREADS, int MINB, int TILE, int MINMODE>
+void run_s(const char* name) {
+  dim3 grid((n + THREADS * Q - 1) / (THREADS * Q), N);
+  cudaFuncAttributes at;
+  cudaFuncGetAttributes(&at, scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE>);
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE>, THREADS, 0);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int it = 0; it < 4; ++it) {
+    cudaMemset(d_flag, 0, 4);
+    cudaEventRecord(e0);
+    scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE><<<grid, THREADS>>>(d_q, d_ps, n, n, d_idx, d_flag);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (it > 0 && ms < best) best = ms;
+  }
+  cudaError_t err = cudaGetLastError();
+  std::vector<int32_t> h((size_t)N * n), r((size_t)N * n);
+  cudaMemcpy(h.data(), d_idx, h.size() * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(r.data(), d_ref, r.size() * 4, cudaMemcpyDeviceToHost);
+  long long mism = 0; for (size_t i = 0; i < h.size(); ++i) mism += h[i] != r[i];
+  unsigned int nf; cudaMemcpy(&nf, d_flag, 4, cudaMemcpyDeviceToHost);
+  const double tf = 8.0 * N * (double)n * n / (best * 1e-3) / 1e12;
+  printf("%-44s regs=%3d occ=%2d CTA/SM  %8.3f ms  %6.2f TFLOP/s(8/eval)  %5.1f%%  mismatch(unfiltered)=%lld flagged=%u (%.3f%%) %s\n", name, at.numRegs, nb, best,
+         tf, 100.0 * tf / 74.45, mism, nf, 100.0 * nf / ((double)N * n), err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1) N = atoi(argv[1]);
+  if (argc > 2) n = atoi(argv[2]);
+  std::vector<float> hq((size_t)N * n * 3), ht((size_t)N * n * 3);
+  srand(1);
+  for (auto& v : ht) v = 40.f * rand() / RAND_MAX - 20.f;
+  for (size_t i = 0; i < hq.size(); ++i) hq[i] = ht[(i + 3 * 977) % ht.size()] + 0.02f * rand() / RAND_MAX;
+  cudaMalloc(&d_q, hq.size() * 4); cudaMalloc(&d_t, ht.size() * 4);
+  cudaMalloc(&d_p, (size_t)N * n * sizeof(RecF32));
+  cudaMalloc(&d_idx, (size_t)N * n * 4); cudaMalloc(&d_ref, (size_t)N * n * 4);
+  cudaMemcpy(d_q, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_t, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
+  pack_kernel<<<dim3((n + 255) / 256, N), 256>>>(d_t, n, d_p);
+  cudaDeviceSynchronize();
+  run<8, 128, 1, 256, 0, false>("Q8  T128 var0 direct (library v2)");
+  cudaMalloc(&d_pe, (size_t)N * n * sizeof(RecE)); cudaMalloc(&d_flag, 4);
+  pack_kernel_e<<<dim3((n + 255) / 256, N), 256>>>(d_t, n, d_pe);
+  cudaDeviceSynchronize();
+  run_e<8, 128, 1, 256, 0>("expanded packed Q8 order0 minb1");
+  cudaMalloc(&d_ps, (size_t)N * n * sizeof(float4));
+  pack_kernel_s<<<dim3((n + 255) / 256, N), 256>>>(d_t, n, d_ps);
+  cudaDeviceSynchronize();
+  run_s<4, 128, 1, 512, 0>("scalar expanded Q4 min3");
+  run_s<4, 128, 1, 512, 1>("scalar expanded Q4 fmin");
+  run_s<8, 128, 1, 512, 0>("scalar expanded Q8 min3");
+  run_s<8, 128, 1, 512, 1>("scalar expanded Q8 fmin");
+  run_s<8, 128, 6, 512, 0>("scalar expanded Q8 min3 minb6");
+  run_s<8, 128, 8, 512, 0>("scalar expanded Q8 min3 minb8");
+  run_s<8, 256, 2, 512, 0>("scalar expanded Q8 T256 min3");
+  run_s<16, 128, 1, 512, 0>("scalar expanded Q16 min3");
+  run_s<16, 128, 4, 512, 0>("scalar expanded Q16 min3 minb4");
+  run_s<12, 128, 1, 512, 0>("scalar expanded Q12 min3");
+  return 0;
+}
