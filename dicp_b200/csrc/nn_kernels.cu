@@ -15,11 +15,12 @@
 // running minimum (FMNMX3, ALU pipe), per query the best chunk, its value and the best value
 // among all *other* chunks.  If that runner-up is further away than a rigorous rounding bound
 // (nn_filter_margin), the nearest neighbour must be inside the best chunk and is found there
-// with the exact direct-form distance; otherwise the query is appended to a list that
-// nn_fallback_f32_kernel resolves exactly (one warp per query, direct form over all targets,
-// warp-shuffle lexicographic argmin).  Either way the result is the direct-form fp32 argmin
-// with torch.argmin's first-minimum tie-break.  Measured on B200: 0.04 % of queries fall back.
-// fp64 (nn_scan_kernel<double>): plain direct-form scan, used by the fp64 parity tests.
+// with the exact direct-form distance; otherwise the query is appended to its pair's list, and
+// the listed queries are rescanned exactly by the direct-form kernel (nn_scan_kernel<float,.,true>,
+// same tiling, records converted back to y in shared memory).  Either way the result is the
+// direct-form fp32 argmin with torch.argmin's first-minimum tie-break.  On the benchmark clouds
+// (|x| up to 28 m) about 1 % of the queries take the fallback.
+// fp64 (nn_scan_kernel<double,.,false>): plain direct-form scan, used by the fp64 parity tests.
 //
 // The target range is split over blockIdx.z when that is needed to fill 148 SMs or to keep the
 // tail wave short; partial (d2, idx) results are merged in split order (earlier split wins ties).
@@ -75,21 +76,33 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-constexpr int NN_THREADS = 128;
+constexpr int NN_THREADS = 128;   // fp64 scan
+constexpr int NN_FB_THREADS = 32; // fp32 exact fallback: one warp per CTA, few queries per pair
 constexpr int NN_TILE = 512;      // records per shared-memory stage
 
-template <typename T, int Q>
-__global__ void __launch_bounds__(NN_THREADS)
+// in-place conversion of a landed fp32 filter record (-2y, |y|^2) to the direct-form record (y, .)
+__device__ __forceinline__ void to_direct_record(float4& v) { v.x *= -0.5f; v.y *= -0.5f; v.z *= -0.5f; }
+__device__ __forceinline__ void to_direct_record(double4&) {}
+
+// Exact direct-form scan.  LIST == false: every query of the pair (fp64 path).  LIST == true: only
+// the queries listed in qlist[b, 0 .. qcount[b]) (the fp32 filter's ambiguous queries), no split.
+template <typename T, int Q, bool LIST, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
                const typename Vec4<T>::type* __restrict__ packed, int n, int m_pad, int tiles_per_split,
                int32_t* __restrict__ idx_out, T* __restrict__ d2_out, T* __restrict__ part_d2,
-               int32_t* __restrict__ part_idx, const int* __restrict__ stop_flag) {
+               int32_t* __restrict__ part_idx, const unsigned int* __restrict__ qcount, const int32_t* __restrict__ qlist,
+               int qcap, unsigned long long* __restrict__ qkey, const int* __restrict__ stop_flag) {
+  constexpr int NN_THREADS = THREADS;
   typedef typename Vec4<T>::type V4;
   if (stop_flag != nullptr && *stop_flag != 0) return;
-  __shared__ __align__(16) V4 tile[2][NN_TILE];
-
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
+  int nq = n;                              // number of queries this pair has for this launch
+  if (LIST) {
+    nq = (int)min(qcount[b], (unsigned int)qcap);
+  }
+  __shared__ __align__(16) V4 tile[2][NN_TILE];
   const int split = blockIdx.z;
   const int N = gridDim.y;
   const V4* tg = packed + (size_t)b * m_pad;
@@ -103,13 +116,18 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
 #pragma unroll
     for (int i = 0; i < 3; ++i) r[i] = (T)rec[ST_R + i];
   }
+  // LIST: the grid's x extent is small and fixed (the list length is only known on the device), so a
+  // CTA walks the list in strides; otherwise the loop body runs once
+  for (int qblk = blockIdx.x * (NN_THREADS * Q); qblk < nq; qblk += gridDim.x * (NN_THREADS * Q)) {
   T x[Q][3], best[Q];
-  int bchunk[Q];
-  const int q0 = blockIdx.x * (NN_THREADS * Q) + tid;
+  int bchunk[Q], qi[Q];
+  const int q0 = qblk + tid;
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
     int i = q0 + k * NN_THREADS;
-    if (i >= n) i = n - 1;
+    if (i >= nq) i = nq - 1;
+    if (LIST) i = qlist[(size_t)b * qcap + i];
+    qi[k] = i;
     const T* p = q + ((size_t)b * n + i) * 3;
     T pv[3] = {p[0], p[1], p[2]};
     if (state != nullptr) {
@@ -142,8 +160,12 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
     const int buf = (t - t_begin) & 1;
     if (t + 1 < t_end) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
-    __syncthreads();
     const int start = t * NN_TILE;
+    if (LIST) {      // each thread rewrites the records it copied itself (visible to it after the wait)
+      const int cnt = min(NN_TILE, m_pad - start);
+      for (int u = tid; u < cnt; u += NN_THREADS) to_direct_record(tile[buf][u]);
+    }
+    __syncthreads();
     const int nchunks = min(NN_TILE, m_pad - start) / NN_CHUNK;
     for (int c = 0; c < nchunks; ++c) {
       T cm[Q];
@@ -166,21 +188,27 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
   // refine: the exact index inside the winning chunk (bit-identical arithmetic)
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
-    const int i = q0 + k * NN_THREADS;
-    if (i >= n) continue;
+    if (q0 + k * NN_THREADS >= nq) continue;
+    const int i = qi[k];
     int found = -1;
     const V4* ch = tg + (size_t)bchunk[k] * NN_CHUNK;
     if (t_begin < t_end) {
 #pragma unroll 4
       for (int j = 0; j < NN_CHUNK; ++j) {
-        const V4 y = ch[j];
+        V4 y = ch[j];
+        if (LIST) to_direct_record(y);
         const T d = dist2<T>(x[k][0], x[k][1], x[k][2], y.x, y.y, y.z);
         if (found < 0 && d == best[k]) found = bchunk[k] * NN_CHUNK + j;
       }
     }
     if (found < 0) found = 0;
     const size_t o = (size_t)b * n + i;
-    if (part_d2 == nullptr) {
+    if (LIST) {
+      // target splits of the fallback merge through a 64-bit atomic minimum on (d2 bits, index):
+      // non-negative floats order like their bit patterns, so this is the lexicographic first minimum
+      if (t_begin < t_end)
+        atomicMin(&qkey[o], ((unsigned long long)__float_as_uint((float)best[k]) << 32) | (unsigned int)found);
+    } else if (part_d2 == nullptr) {
       idx_out[o] = found;
       if (d2_out != nullptr) d2_out[o] = best[k];
     } else {
@@ -188,6 +216,7 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
       part_idx[((size_t)split * N) * n + o] = found;
     }
   }
+  }   // query-block loop
 }
 
 // ---------------------------------------------------------------------------------------
@@ -203,15 +232,25 @@ __device__ __forceinline__ float dist2_rec(float x0, float x1, float x2, const f
 constexpr int NNF_THREADS = 128;
 constexpr int NNF_TILE = 512;     // records per shared-memory stage (8 KB)
 
-// Bound on |v_j - (d_j^2 - |x|^2)| for every target whose norm is at most r, plus the rounding of
-// the direct-form distance it is compared with: h carries u|y|^2, the three
-// FMAs u(|y|^2 + 2|x||y|) each; the constants are inflated for the roundings of this bound itself.
-__device__ __forceinline__ float nn_filter_margin(float xx, float v_best) {
+// Filter margin of one query.  u = 2^-24.  The filter value of target y is
+//   v = fl(x0*a0 + fl(x1*a1 + fl(x2*a2 + h))),  a = -2y exactly, h = fl(|y|^2) (rounded once from fp64),
+// so |v - (d^2 - |x|^2)| <= u (|y|^2 + |s1| + |s2| + |s3|) (1 + 4u) with the exact partial sums
+//   s1 = |y|^2 - 2 x2 y2,  s2 = s1 - 2 x1 y1,  s3 = s2 - 2 x0 y0.
+// Only targets within rho = 2 d_best of the query can beat the best one, and for those each |s_i|
+// differs from its value at y = x (|x|^2 - 2 x2^2, ... , -|x|^2) by at most (2|x| + 2(|x_2|+..)) rho + rho^2.
+// A target in another chunk can only be the true (direct-form fp32) nearest neighbour if its filter
+// value is within  E_other + E_best + 10 u d_best^2  of the best chunk's; the constants below are
+// inflated for the rounding of this bound itself.
+__device__ __forceinline__ float nn_filter_margin(float x0, float x1, float x2, float v_best) {
   const float U = 5.9604645e-8f;                                   // 2^-24
+  const float xx = x0 * x0 + x1 * x1 + x2 * x2;
   const float xn = sqrtf(xx);
   const float d2 = fmaxf(v_best + xx, 0.0f);
-  const float r = xn + 2.0f * sqrtf(d2) + 1.0e-3f * xn + 1.0e-30f;   // |y| <= |x| + 2 d_best covers every target that can win
-  return 3.0f * U * (4.0f * r * r + 6.0f * xn * r) + 16.0f * U * d2;
+  const float rho = 2.0f * sqrtf(d2) + 1.0e-3f * xn + 1.0e-30f;
+  const float s1 = fabsf(xx - 2.0f * x2 * x2);
+  const float s2 = fabsf(xx - 2.0f * x2 * x2 - 2.0f * x1 * x1);
+  const float E = U * ((xn + rho) * (xn + rho) + s1 + s2 + xx + 14.5f * xn * rho + 3.0f * rho * rho);
+  return 2.1f * E + 16.0f * U * d2;
 }
 
 template <int Q>
@@ -219,7 +258,8 @@ __global__ void __launch_bounds__(NNF_THREADS, 1)
 nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n,
                    int m_pad, int tiles_per_split, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
                    float* __restrict__ part_d2, int32_t* __restrict__ part_idx, unsigned int* __restrict__ fb_count,
-                   long long* __restrict__ fb_list, const int* __restrict__ stop_flag) {
+                   int32_t* __restrict__ fb_list, int fb_cap, unsigned long long* __restrict__ fb_key,
+                   const int* __restrict__ stop_flag) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   __shared__ __align__(16) float4 tile[2][NNF_TILE];
   const float INF = Sentinel<float>::inf();
@@ -320,8 +360,11 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
     int found = 0;
     float bd = INF;
     if (t_begin < t_end) {
-      const float xx = x[k][0] * x[k][0] + x[k][1] * x[k][1] + x[k][2] * x[k][2];
-      if (!(second[k] - best[k] > nn_filter_margin(xx, best[k]))) fb_list[atomicAdd(fb_count, 1u)] = (long long)o;
+      if (!(second[k] - best[k] > nn_filter_margin(x[k][0], x[k][1], x[k][2], best[k]))) {
+        const unsigned int slot = atomicAdd(&fb_count[b], 1u);
+        if (slot < (unsigned int)fb_cap) fb_list[(size_t)b * fb_cap + slot] = i;
+        fb_key[o] = 0xffffffffffffffffull;
+      }
       const float4* ch = tg + (size_t)bchunk[k] * NN_CHUNK;
 #pragma unroll 4
       for (int j = 0; j < NN_CHUNK; ++j) {
@@ -339,46 +382,18 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
   }
 }
 
-// exact fallback: one warp per flagged query, lanes stride over all targets with the direct form,
-// lexicographic (d2, index) warp-shuffle argmin => first minimum
-__global__ void __launch_bounds__(256)
-nn_fallback_f32_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n,
-                       int m_pad, const unsigned int* __restrict__ fb_count, const long long* __restrict__ fb_list,
-                       int32_t* __restrict__ idx_out, float* __restrict__ d2_out, const int* __restrict__ stop_flag) {
+// writes the fallback's (d2, index) keys of the listed queries to the outputs
+__global__ void nn_fallback_unpack_kernel(const unsigned int* __restrict__ qcount, const int32_t* __restrict__ qlist, int qcap, int n,
+                                          const unsigned long long* __restrict__ qkey, int32_t* __restrict__ idx_out,
+                                          float* __restrict__ d2_out, const int* __restrict__ stop_flag) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
-  const unsigned int count = *fb_count;
-  const int lane = threadIdx.x & 31;
-  const unsigned int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (unsigned int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += warps_total) {
-    const long long o = fb_list[w];
-    const int b = (int)(o / n);
-    const float* p = q + (size_t)o * 3;
-    float x0 = p[0], x1 = p[1], x2 = p[2];
-    if (state != nullptr) {
-      const double* rec = state + (size_t)b * ST_STRIDE;
-      float C[9], pv[3] = {x0, x1, x2}, a[3];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) C[i] = (float)rec[ST_C + i];
-      rotate(C, pv, a);
-      x0 = a[0] + (float)rec[ST_R]; x1 = a[1] + (float)rec[ST_R + 1]; x2 = a[2] + (float)rec[ST_R + 2];
-    }
-    const float4* tg = packed + (size_t)b * m_pad;
-    float bd = Sentinel<float>::inf();
-    int bi = 0x7fffffff;
-    for (int j = lane; j < m_pad; j += 32) {
-      const float d = dist2_rec(x0, x1, x2, tg[j]);
-      if (d < bd) { bd = d; bi = j; }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, bd, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-    }
-    if (lane == 0) {
-      idx_out[o] = bi == 0x7fffffff ? 0 : bi;
-      if (d2_out != nullptr) d2_out[o] = bd;
-    }
+  const int b = blockIdx.y;
+  const int cnt = (int)min(qcount[b], (unsigned int)qcap);
+  for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < cnt; slot += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * n + qlist[(size_t)b * qcap + slot];
+    const unsigned long long key = qkey[o];
+    idx_out[o] = (int32_t)(key & 0xffffffffull);
+    if (d2_out != nullptr) d2_out[o] = __uint_as_float((unsigned int)(key >> 32));
   }
 }
 
@@ -434,19 +449,22 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
 }
 
 // workspace of one search: [split partials d2 | split partials idx] [fallback counter] [fallback list]
-struct NNWorkspace { void* part_d2; int32_t* part_idx; unsigned int* fb_count; long long* fb_list; size_t total; };
+struct NNWorkspace { void* part_d2; int32_t* part_idx; unsigned int* fb_count; int32_t* fb_list; int fb_cap; unsigned long long* fb_key; size_t total; };
 static NNWorkspace nn_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size) {
   const NNPlan p = nn_plan(N, n, m, elem_size);
   Arena ar(ws, ws_bytes);
   NNWorkspace w;
-  w.part_d2 = nullptr; w.part_idx = nullptr; w.fb_count = nullptr; w.fb_list = nullptr;
+  w.part_d2 = nullptr; w.part_idx = nullptr; w.fb_count = nullptr; w.fb_list = nullptr; w.fb_key = nullptr;
   if (p.nsplit > 1) {
     w.part_d2 = ar.take<char>((size_t)p.nsplit * N * n * elem_size);
     w.part_idx = ar.take<int32_t>((size_t)p.nsplit * N * n);
   }
+  w.fb_cap = 0;
   if (elem_size == 4) {
-    w.fb_count = ar.take<unsigned int>(1);
-    w.fb_list = ar.take<long long>((size_t)N * n * p.nsplit);     // every (query, split) can flag at most once
+    w.fb_cap = n * p.nsplit;                                       // every (query, split) can flag at most once
+    w.fb_count = ar.take<unsigned int>(N);                         // per pair
+    w.fb_list = ar.take<int32_t>((size_t)N * w.fb_cap);            // per pair: query indices
+    w.fb_key = ar.take<unsigned long long>((size_t)N * n);         // per query: (d2 bits << 32 | index) of the exact rescan
   }
   w.total = ar.off;
   return w;
@@ -457,31 +475,48 @@ size_t nn_search_ws_bytes(int N, int n, int m, int elem_size) { return nn_ws_lay
 static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_t st, const float* q, const double* state, const float4* packed,
                        int n, int m_pad, int32_t* idx_out, float* d2_out, const int* stop_flag) {
   dim3 grid(p.gx, N, p.nsplit);
-  DICP_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(unsigned int), st));
+  DICP_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(unsigned int) * N, st));
   if (p.q == 16)
     nn_scan_f32_kernel<16><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
-                                                          w.part_idx, w.fb_count, w.fb_list, stop_flag);
+                                                          w.part_idx, w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
   else
     nn_scan_f32_kernel<8><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
-                                                         w.part_idx, w.fb_count, w.fb_list, stop_flag);
+                                                         w.part_idx, w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
   DICP_LAUNCH_CHECK();
   return 0;
 }
 static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_t st, const double* q, const double* state, const double4* packed,
                        int n, int m_pad, int32_t* idx_out, double* d2_out, const int* stop_flag) {
   dim3 grid(p.gx, N, p.nsplit);
-  nn_scan_kernel<double, 2><<<grid, NN_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (double*)w.part_d2,
-                                                         w.part_idx, stop_flag);
+  nn_scan_kernel<double, 2, false, NN_THREADS><<<grid, NN_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out,
+                                                                            (double*)w.part_d2, w.part_idx, nullptr, nullptr, 0, nullptr, stop_flag);
   DICP_LAUNCH_CHECK();
   return 0;
 }
-static int launch_fallback(const NNWorkspace& w, cudaStream_t st, const float* q, const double* state, const float4* packed, int n, int m_pad,
+// exact fallback for the fp32 filter's ambiguous queries: direct-form rescan of the per-pair lists.
+// One warp per CTA (a pair rarely lists more than a few dozen queries), the target range split over
+// blockIdx.z so that the whole machine works on it; splits merge through atomicMin on fb_key.
+constexpr int NN_FB_Q = 2;
+static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const float* q, const double* state, const float4* packed, int n, int m_pad,
                            int32_t* idx_out, float* d2_out, const int* stop_flag) {
-  nn_fallback_f32_kernel<<<148 * 4, 256, 0, st>>>(q, state, packed, n, m_pad, w.fb_count, w.fb_list, idx_out, d2_out, stop_flag);
+  const int tiles_total = (m_pad + NN_TILE - 1) / NN_TILE;
+  int fs = tiles_total / 4;
+  if (fs > 8) fs = 8;
+  if (fs < 1) fs = 1;
+  const int tps = (tiles_total + fs - 1) / fs;
+  fs = (tiles_total + tps - 1) / tps;
+  int gx = (w.fb_cap + NN_FB_THREADS * NN_FB_Q - 1) / (NN_FB_THREADS * NN_FB_Q);
+  if (gx > 4) gx = 4;                        // CTAs stride over longer lists; empty CTAs are not free
+  dim3 grid(gx, N, fs);
+  nn_scan_kernel<float, NN_FB_Q, true, NN_FB_THREADS><<<grid, NN_FB_THREADS, 0, st>>>(q, state, packed, n, m_pad, tps, idx_out, d2_out, nullptr, nullptr,
+                                                                                      w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
+  DICP_LAUNCH_CHECK();
+  dim3 ugrid(1, N);
+  nn_fallback_unpack_kernel<<<ugrid, 256, 0, st>>>(w.fb_count, w.fb_list, w.fb_cap, n, w.fb_key, idx_out, d2_out, stop_flag);
   DICP_LAUNCH_CHECK();
   return 0;
 }
-static int launch_fallback(const NNWorkspace&, cudaStream_t, const double*, const double*, const double4*, int, int, int32_t*, double*, const int*) {
+static int launch_fallback(const NNWorkspace&, int, cudaStream_t, const double*, const double*, const double4*, int, int, int32_t*, double*, const int*) {
   return 0;   // the fp64 scan is exact (direct form)
 }
 
@@ -500,7 +535,7 @@ int nn_search(const T* q, const double* state, const typename Vec4<T>::type* pac
     nn_merge_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)w.part_d2, w.part_idx, total, p.nsplit, idx_out, d2_out, stop_flag);
     DICP_LAUNCH_CHECK();
   }
-  return launch_fallback(w, st, q, state, packed, n, m_pad, idx_out, d2_out, stop_flag);
+  return launch_fallback(w, N, st, q, state, packed, n, m_pad, idx_out, d2_out, stop_flag);
 }
 template int nn_search<float>(const float*, const double*, const float4*, int, int, int, int32_t*, float*, const int*, void*, size_t, cudaStream_t);
 template int nn_search<double>(const double*, const double*, const double4*, int, int, int, int32_t*, double*, const int*, void*, size_t, cudaStream_t);
