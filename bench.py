@@ -186,13 +186,16 @@ def roofline_nn(src, tgt, pk):
         _lib.check(lib.dicp_nn_scan_f32(_lib.ptr(src), _lib.ptr(packed), N, n, m, _lib.ptr(idx), None, _lib.ptr(ws), ws.numel(), st), "scan")
 
     sec = time_kernel(launch, reps=5)
-    flop = 8.0 * N * n * m                   # 3 sub, 3 mul, 2 add per (query, target) evaluation
+    evals = float(N) * n * m
+    flop = 8.0 * evals                       # algorithmic: 3 sub, 3 mul, 2 add per (query, target) evaluation
     peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     ach = flop / sec / 1e12
-    return {"kernel": "nn_scan_kernel<float,4>", "bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak, "traffic": None, "ms_per_launch": sec * 1e3,
+    executed = 6.0 * evals / sec / 1e12      # what the filter scan issues: 3 FFMA per evaluation (refine + fallback < 2 % more)
+    return {"kernel": "nn_scan_f32_kernel<16> + merge + exact fallback (one dicp_nn_scan_f32 call)", "bound": "fp32",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms_per_launch": sec * 1e3,
+            "executed_tflops": executed, "frac_executed": executed / peak,
             "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],
-            "flop_per_pair_eval": 8, "units_per_launch": float(N) * n * m}, idx
+            "flop_per_pair_eval": {"algorithmic": 8, "executed": 6}, "units_per_launch": evals}, idx
 
 
 def roofline_gn(src, tgt, idx, pk):
@@ -320,8 +323,9 @@ def run_ours(args):
             cpu = {"value": reps / cdt, "unit": "pairs/s", "cores": cores, "kind": "port",
                    "sample": "%d x 1 pair of the C3 workload (fwd+bwd, 10 it), oracle port of the reference torch-CPU path, "
                              "%d threads, %.1f s" % (reps, torch.get_num_threads(), cdt)}
-        # kernels of libdicp_b200.so per step: forward init+pack+10x(nn,gn,update)+finalize = 33, backward seed+10x(pair,points)+finish = 22
-        launches_per_step = (2 + 3 * ITERS + 1) + (1 + 2 * ITERS + 1)
+        # kernels of libdicp_b200.so per step: forward init + pack + 10 x (scan, merge, fallback, unpack, gn, update) + finalize,
+        # backward seed + 10 x (pair, points) + finish
+        launches_per_step = (2 + 6 * ITERS + 1) + (1 + 2 * ITERS + 1)
         h2d = src_h.numel() * 4 + tgt_h.numel() * 4 + T0_h.numel() * 4 + 12 * 4
         d2h = 13 * 4 + PAIRS_PER_GPU * 16 * 4
         line = {

@@ -83,7 +83,7 @@ size_t nn_workspace_bytes(int N, int n, int m, int elem_size);
 template <typename T> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
-constexpr int NN_CHUNK = 16;
+constexpr int NN_CHUNK = 32;
 inline int nn_m_pad(int m) { return (m + NN_CHUNK - 1) / NN_CHUNK * NN_CHUNK; }
 inline size_t nn_packed_bytes(int N, int m, int elem_size) { return align_up((size_t)N * nn_m_pad(m) * 4 * elem_size); }
 

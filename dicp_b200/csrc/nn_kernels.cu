@@ -423,10 +423,10 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
   const int m_pad = nn_m_pad(m);
   int ctas_per_sm;
   if (elem_size == 4) {
-    // 16 queries per thread (2 CTAs / SM) once there is enough work for >= 8 waves of them, else 8 (4 CTAs / SM)
+    // 16 queries per thread (2 CTAs / SM) once there is enough work for >= 4 waves of them, else 8 (4 CTAs / SM)
     p.threads = NNF_THREADS; p.tile = NNF_TILE;
     const long long ctas16 = (long long)N * ((n + NNF_THREADS * 16 - 1) / (NNF_THREADS * 16));
-    p.q = ctas16 >= 148LL * 2 * 8 ? 16 : 8;
+    p.q = ctas16 >= 148LL * 2 * 4 ? 16 : 8;
     ctas_per_sm = p.q == 16 ? 2 : 4;
   } else {
     p.threads = NN_THREADS; p.tile = NN_TILE; p.q = 2; ctas_per_sm = 4;

@@ -76,9 +76,10 @@ DICP_API const char* dicp_last_error(void);
  * tgt [N,m,S]   targets, S in {3,6}; only the first 3 columns are used
  * idx_out [N,n] int32 index of the nearest target (first minimum on exact ties)
  * d2_out  [N,n] squared distance to it, or NULL
- * Distances are evaluated in the direct form (x-y)^2 in the element type, so the result
- * equals the exact-arithmetic argmin whenever the relative gap between the two smallest
- * squared distances exceeds a few ulp.                                                  */
+ * The result is the argmin of the direct-form distance (x-y)^2 evaluated in the element type
+ * (fp32: found through an expanded-form filter with a rigorous error margin, then refined /
+ * rescanned exactly), so it equals the exact-arithmetic argmin whenever the relative gap
+ * between the two smallest squared distances exceeds a few ulp.                          */
 DICP_API size_t dicp_nn_workspace_bytes(int N, int n, int m, int elem_size);
 DICP_API int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, int m, int S,
                        int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
@@ -87,8 +88,9 @@ DICP_API int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n
 
 /* The two stages of dicp_nn_argmin_*, exported for profiling and for callers that search the
  * same targets repeatedly (the solver loop packs once per call): pack the targets into
- * 16-byte (x,y,z,0) records padded to a multiple of 16 (`dicp_nn_packed_bytes` bytes), then
- * scan.  `ws` for the scan is sized by dicp_nn_workspace_bytes.                           */
+ * records padded with sentinels to a multiple of 32 rows (`dicp_nn_packed_bytes` bytes; fp32:
+ * 16-byte (-2x,-2y,-2z,|y|^2), fp64: 32-byte (x,y,z,0)), then scan.  `ws` for the scan is sized
+ * by dicp_nn_workspace_bytes.                                                              */
 DICP_API size_t dicp_nn_packed_bytes(int N, int m, int elem_size);
 DICP_API int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream);
 DICP_API int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void* stream);

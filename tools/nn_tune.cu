@@ -350,7 +350,7 @@ __global__ void pack_kernel_s(const float* tgt, int m, float4* packed) {
   const double h = (double)r[0] * r[0] + (double)r[1] * r[1] + (double)r[2] * r[2];
   packed[(size_t)b * m + j] = make_float4(-2.f * r[0], -2.f * r[1], -2.f * r[2], (float)h);
 }
-template <int Q, int THREADS, int MINB, int TILE, int MINMODE>
+template <int Q, int THREADS, int MINB, int TILE, int MINMODE, int CH = 16>
 __global__ void __launch_bounds__(THREADS, MINB)
 scan_scalar_e(const float* __restrict__ q, const float4* __restrict__ packed, int n, int m_pad, int32_t* __restrict__ idx_out,
               unsigned int* __restrict__ nflag) {
@@ -384,14 +384,14 @@ scan_scalar_e(const float* __restrict__ q, const float4* __restrict__ packed, in
     else cp_async_wait<0>();
     __syncthreads();
     const int start = t * TILE;
-    const int nchunks = min(TILE, m_pad - start) / CHUNK;
+    const int nchunks = min(TILE, m_pad - start) / CH;
     for (int c = 0; c < nchunks; ++c) {
       float cm[Q];
 #pragma unroll
       for (int k = 0; k < Q; ++k) cm[k] = INF;
-      const float4* ch = &tile[buf][c * CHUNK];
+      const float4* ch = &tile[buf][c * CH];
 #pragma unroll
-      for (int j = 0; j < CHUNK; j += 2) {
+      for (int j = 0; j < CH; j += 2) {
         const float4 a0 = ch[j], a1 = ch[j + 1];
         float v0[Q], v1[Q];
 #pragma unroll
@@ -415,7 +415,7 @@ scan_scalar_e(const float* __restrict__ q, const float4* __restrict__ packed, in
 #pragma unroll
       for (int k = 0; k < Q; ++k) {
         second[k] = fminf(second[k], fmaxf(cm[k], best[k]));
-        if (cm[k] < best[k]) { best[k] = cm[k]; bchunk[k] = start / CHUNK + c; }
+        if (cm[k] < best[k]) { best[k] = cm[k]; bchunk[k] = start / CH + c; }
       }
     }
     __syncthreads();
@@ -431,11 +431,11 @@ scan_scalar_e(const float* __restrict__ q, const float4* __restrict__ packed, in
     const float E = 14.0f * U * (sqrtf(xx) + r) * (sqrtf(xx) + r);
     if (!(second[k] - best[k] > 2.0f * E)) atomicAdd(nflag, 1u);
     int found = -1; float bd = INF;
-    const float4* ch = tg + (size_t)bchunk[k] * CHUNK;
-    for (int j = 0; j < CHUNK; ++j) {
+    const float4* ch = tg + (size_t)bchunk[k] * CH;
+    for (int j = 0; j < CH; ++j) {
       const float4 a = ch[j];
       const float d = dist2_rec(x[k][0], x[k][1], x[k][2], 0.5f * a.x, 0.5f * a.y, 0.5f * a.z);
-      if (d < bd) { bd = d; found = bchunk[k] * CHUNK + j; }
+      if (d < bd) { bd = d; found = bchunk[k] * CH + j; }
     }
     idx_out[(size_t)b * n + i] = found < 0 ? 0 : found;
   }
@@ -521,19 +521,19 @@ void run_e(const char* name) {
 }
 
 static float4* d_ps;
-template <int Q, int THREADS, int MINB, int TILE, int MINMODE>
+template <int Q, int THREADS, int MINB, int TILE, int MINMODE, int CH = 16>
 void run_s(const char* name) {
   dim3 grid((n + THREADS * Q - 1) / (THREADS * Q), N);
   cudaFuncAttributes at;
-  cudaFuncGetAttributes(&at, scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE>);
+  cudaFuncGetAttributes(&at, scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE, CH>);
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE>, THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE, CH>, THREADS, 0);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 1e30f;
   for (int it = 0; it < 4; ++it) {
     cudaMemset(d_flag, 0, 4);
     cudaEventRecord(e0);
-    scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE><<<grid, THREADS>>>(d_q, d_ps, n, n, d_idx, d_flag);
+    scan_scalar_e<Q, THREADS, MINB, TILE, MINMODE, CH><<<grid, THREADS>>>(d_q, d_ps, n, n, d_idx, d_flag);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (it > 0 && ms < best) best = ms;
@@ -567,19 +567,19 @@ int main(int argc, char** argv) {
   cudaMalloc(&d_pe, (size_t)N * n * sizeof(RecE)); cudaMalloc(&d_flag, 4);
   pack_kernel_e<<<dim3((n + 255) / 256, N), 256>>>(d_t, n, d_pe);
   cudaDeviceSynchronize();
-  run_e<8, 128, 1, 256, 0>("expanded packed Q8 order0 minb1");
   cudaMalloc(&d_ps, (size_t)N * n * sizeof(float4));
   pack_kernel_s<<<dim3((n + 255) / 256, N), 256>>>(d_t, n, d_ps);
   cudaDeviceSynchronize();
-  run_s<4, 128, 1, 512, 0>("scalar expanded Q4 min3");
-  run_s<4, 128, 1, 512, 1>("scalar expanded Q4 fmin");
-  run_s<8, 128, 1, 512, 0>("scalar expanded Q8 min3");
-  run_s<8, 128, 1, 512, 1>("scalar expanded Q8 fmin");
-  run_s<8, 128, 6, 512, 0>("scalar expanded Q8 min3 minb6");
-  run_s<8, 128, 8, 512, 0>("scalar expanded Q8 min3 minb8");
-  run_s<8, 256, 2, 512, 0>("scalar expanded Q8 T256 min3");
-  run_s<16, 128, 1, 512, 0>("scalar expanded Q16 min3");
-  run_s<16, 128, 4, 512, 0>("scalar expanded Q16 min3 minb4");
-  run_s<12, 128, 1, 512, 0>("scalar expanded Q12 min3");
+  run_s<8, 128, 1, 512, 0, 16>("scalar expanded Q8  ch16 tile512");
+  run_s<8, 128, 1, 512, 0, 32>("scalar expanded Q8  ch32 tile512");
+  run_s<8, 128, 1, 1024, 0, 32>("scalar expanded Q8  ch32 tile1024");
+  run_s<16, 128, 1, 512, 0, 16>("scalar expanded Q16 ch16 tile512");
+  run_s<16, 128, 1, 512, 0, 32>("scalar expanded Q16 ch32 tile512");
+  run_s<16, 128, 1, 1024, 0, 32>("scalar expanded Q16 ch32 tile1024");
+  run_s<16, 128, 1, 1024, 0, 64>("scalar expanded Q16 ch64 tile1024");
+  run_s<16, 64, 1, 512, 0, 32>("scalar expanded Q16 T64 ch32");
+  run_s<16, 256, 1, 512, 0, 32>("scalar expanded Q16 T256 ch32");
+  run_s<20, 128, 1, 512, 0, 32>("scalar expanded Q20 ch32");
+  run_s<24, 128, 1, 512, 0, 32>("scalar expanded Q24 ch32");
   return 0;
 }
