@@ -16,17 +16,17 @@
 
 namespace dicp {
 
-constexpr int BW_THREADS = 256;
+constexpr int BW_THREADS = 128;
 
-template <int NV>
-__device__ __forceinline__ void bw_block_reduce_store(double* vals, double* out, double* smem) {
+template <typename T, int NV>
+__device__ __forceinline__ void bw_block_reduce_store(const T* vals, double* out, double* smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    double x = vals[v];
+    T x = vals[v];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) smem[warp * NV + v] = x;
+    if (lane == 0) smem[warp * NV + v] = (double)x;
   }
   __syncthreads();
   if (threadIdx.x < NV) {
@@ -69,10 +69,7 @@ bwd_seed_kernel(const T* __restrict__ source, const T* __restrict__ grad_pc, con
       acc[9 + rr] += g[rr];
     }
   }
-  double vals[BW_NRED];
-#pragma unroll
-  for (int i = 0; i < BW_NRED; ++i) vals[i] = (double)acc[i];
-  bw_block_reduce_store<BW_NRED>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * BW_NRED, red_smem);
+  bw_block_reduce_store<T, BW_NRED>(acc, partials + ((size_t)b * gridDim.x + blockIdx.x) * BW_NRED, red_smem);
 }
 
 // mode 0: first step (k = K-1): carry = grad_T + partial sums, then update-step adjoint
@@ -141,40 +138,55 @@ bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, co
     T* gt_b = grad_target + (size_t)b * m * S;
     T* gs_b = grad_source + (size_t)b * n * 3;
     const int32_t* idx_b = idx + (size_t)b * n;
-    for (int i = blockIdx.x * BW_THREADS + threadIdx.x; i < n; i += gridDim.x * BW_THREADS) {
-      const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
-      const int j = idx_b[i];
-      const T* row = tgt_b + (size_t)j * S;
-      const T q[3] = {row[0], row[1], row[2]};
-      T nr[3] = {T(0), T(0), T(0)};
-      if (PT2PL) { nr[0] = row[3]; nr[1] = row[4]; nr[2] = row[5]; }
-      const T w0 = w_init != nullptr ? w_init[(size_t)b * n + i] : T(1);
-      PointEval<T> s;
-      eval_point<T, PT2PL>(C, r, p, q, nr, w0, P, s);
-      T abar[3], ebar[3], nbar[3], w0bar;
-      point_backward<T, PT2PL>(s, w0, lam, del, abar, ebar, nbar, w0bar);
-      if (grad_w != nullptr) grad_w[(size_t)b * n + i] += w0bar;
+    // U correspondences per thread and pass, loads hoisted ahead of the arithmetic (see gn_accum_kernel)
+    constexpr int U = sizeof(T) == 4 ? 4 : 2;
+    for (int base = blockIdx.x * (BW_THREADS * U); base < n; base += gridDim.x * (BW_THREADS * U)) {
+      int ii[U], jj[U];
+      T p[U][3], q[U][3], nr[U][3], w0[U];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gs_b[3 * i + c] += C[c] * abar[0] + C[3 + c] * abar[1] + C[6 + c] * abar[2];   // C^T abar
-      T* grow = gt_b + (size_t)j * S;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) atomicAdd(grow + c, -ebar[c]);
-      if (PT2PL) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(grow + 3 + c, nbar[c]);
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * BW_THREADS + threadIdx.x;
+        ii[u] = i < n ? i : -1;
+        const int ic = i < n ? i : n - 1;
+        jj[u] = idx_b[ic];
+        p[u][0] = src_b[3 * ic]; p[u][1] = src_b[3 * ic + 1]; p[u][2] = src_b[3 * ic + 2];
+        w0[u] = w_init != nullptr ? w_init[(size_t)b * n + ic] : T(1);
       }
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) {
+      for (int u = 0; u < U; ++u) {
+        const T* row = tgt_b + (size_t)jj[u] * S;
+        q[u][0] = row[0]; q[u][1] = row[1]; q[u][2] = row[2];
+        if (PT2PL) { nr[u][0] = row[3]; nr[u][1] = row[4]; nr[u][2] = row[5]; }
+        else { nr[u][0] = nr[u][1] = nr[u][2] = T(0); }
+      }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) acc[rr * 3 + c] += abar[rr] * p[c];
-        acc[9 + rr] += ebar[rr];
+      for (int u = 0; u < U; ++u) {
+        if (ii[u] < 0) continue;
+        const int i = ii[u];
+        PointEval<T> s;
+        eval_point<T, PT2PL>(C, r, p[u], q[u], nr[u], w0[u], P, s);
+        T abar[3], ebar[3], nbar[3], w0bar;
+        point_backward<T, PT2PL>(s, w0[u], lam, del, abar, ebar, nbar, w0bar);
+        if (grad_w != nullptr) grad_w[(size_t)b * n + i] += w0bar;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gs_b[3 * i + c] += C[c] * abar[0] + C[3 + c] * abar[1] + C[6 + c] * abar[2];   // C^T abar
+        T* grow = gt_b + (size_t)jj[u] * S;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(grow + c, -ebar[c]);
+        if (PT2PL) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) atomicAdd(grow + 3 + c, nbar[c]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[rr * 3 + c] += abar[rr] * p[u][c];
+          acc[9 + rr] += ebar[rr];
+        }
       }
     }
   }
-  double vals[BW_NRED];
-#pragma unroll
-  for (int i = 0; i < BW_NRED; ++i) vals[i] = (double)acc[i];
-  bw_block_reduce_store<BW_NRED>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * BW_NRED, red_smem);
+  bw_block_reduce_store<T, BW_NRED>(acc, partials + ((size_t)b * gridDim.x + blockIdx.x) * BW_NRED, red_smem);
 }
 
 template <typename T>

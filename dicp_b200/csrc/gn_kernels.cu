@@ -27,8 +27,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int GN_THREADS = 256;
-constexpr int GN_PTS_PER_THREAD = 4;
+constexpr int GN_THREADS = 128;
+constexpr int GN_PTS_PER_THREAD = 8;   // 2 passes of 4: amortises the 31-value block reduction
 
 int gn_blocks_per_pair(int n) {
   int nb = (n + GN_THREADS * GN_PTS_PER_THREAD - 1) / (GN_THREADS * GN_PTS_PER_THREAD);
@@ -37,17 +37,18 @@ int gn_blocks_per_pair(int n) {
   return nb;
 }
 
-// block-wide sum of NV per-thread values (in double); result lands in out[0..NV) of the
-// CTA's partial row.  Fixed tree => deterministic for a given launch shape.
-template <int NV>
-__device__ __forceinline__ void block_reduce_store(double* vals, double* out, double* smem /* [warps][NV] */) {
+// block-wide sum of NV per-thread values: warp shuffle tree in the compute type (32 partials of
+// a handful of terms each), then double across warps; result lands in out[0..NV) of the CTA's
+// partial row.  Fixed tree => deterministic for a given launch shape.
+template <typename T, int NV>
+__device__ __forceinline__ void block_reduce_store(const T* vals, double* out, double* smem /* [warps][NV] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    double x = vals[v];
+    T x = vals[v];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) smem[warp * NV + v] = x;
+    if (lane == 0) smem[warp * NV + v] = (double)x;
   }
   __syncthreads();
   if (threadIdx.x < NV) {
@@ -57,6 +58,10 @@ __device__ __forceinline__ void block_reduce_store(double* vals, double* out, do
   }
 }
 
+template <typename T> struct GnUnroll;
+template <> struct GnUnroll<float> { static constexpr int U = 4; };
+template <> struct GnUnroll<double> { static constexpr int U = 2; };
+
 template <typename T, bool PT2PL, int DIM>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
@@ -65,6 +70,7 @@ gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, cons
                 double* __restrict__ partials, const int* __restrict__ stop_flag) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   __shared__ double red_smem[(GN_THREADS / 32) * RED_N];
+  constexpr int U = GnUnroll<T>::U;
   const int b = blockIdx.y;
   const double* rec = state + (size_t)b * ST_STRIDE;
   T C[9], r[3];
@@ -84,25 +90,40 @@ gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, cons
   constexpr int R = PT2PL ? 1 : 3;
   T* wout = weights_out != nullptr ? weights_out + (size_t)b * w_pair_stride : nullptr;
 
-  for (int i = blockIdx.x * GN_THREADS + threadIdx.x; i < n; i += gridDim.x * GN_THREADS) {
-    const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
-    const T* row = tgt_b + (size_t)idx_b[i] * S;
-    const T q[3] = {row[0], row[1], row[2]};
-    T nr[3] = {T(0), T(0), T(0)};
-    if (PT2PL) { nr[0] = row[3]; nr[1] = row[4]; nr[2] = row[5]; }
-    const T w0 = (w_init != nullptr ? w_init[(size_t)b * n + i] : T(1)) * active;      // ICP.py:257
-    PointEval<T> s;
-    eval_point<T, PT2PL>(C, r, p, q, nr, w0, P, s);
-    accum_point<T, PT2PL, DIM>(acc, s, w0, P.thresh);
-    if (wout != nullptr) {
+  // U correspondences per thread and pass; all index / point / row loads of a pass are issued
+  // before any arithmetic so that U dependent gathers are in flight per thread (HBM latency bound)
+  for (int base = blockIdx.x * (GN_THREADS * U); base < n; base += gridDim.x * (GN_THREADS * U)) {
+    int ii[U], jj[U];
+    T p[U][3], q[U][3], nr[U][3], w0[U];
 #pragma unroll
-      for (int k = 0; k < R; ++k) wout[(size_t)i * R + k] = s.w;                        // ICP.py:222, 164-165
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * GN_THREADS + threadIdx.x;
+      ii[u] = i < n ? i : -1;
+      const int ic = i < n ? i : n - 1;
+      jj[u] = idx_b[ic];
+      p[u][0] = src_b[3 * ic]; p[u][1] = src_b[3 * ic + 1]; p[u][2] = src_b[3 * ic + 2];
+      w0[u] = (w_init != nullptr ? w_init[(size_t)b * n + ic] : T(1)) * active;          // ICP.py:257
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const T* row = tgt_b + (size_t)jj[u] * S;
+      q[u][0] = row[0]; q[u][1] = row[1]; q[u][2] = row[2];
+      if (PT2PL) { nr[u][0] = row[3]; nr[u][1] = row[4]; nr[u][2] = row[5]; }
+      else { nr[u][0] = nr[u][1] = nr[u][2] = T(0); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ii[u] < 0) continue;
+      PointEval<T> s;
+      eval_point<T, PT2PL>(C, r, p[u], q[u], nr[u], w0[u], P, s);
+      accum_point<T, PT2PL, DIM>(acc, s, w0[u], P.thresh);
+      if (wout != nullptr) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) wout[(size_t)ii[u] * R + k] = s.w;                      // ICP.py:222, 164-165
+      }
     }
   }
-  double vals[RED_N];
-#pragma unroll
-  for (int i = 0; i < RED_N; ++i) vals[i] = (double)acc[i];
-  block_reduce_store<RED_N>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * RED_N, red_smem);
+  block_reduce_store<T, RED_N>(acc, partials + ((size_t)b * gridDim.x + blockIdx.x) * RED_N, red_smem);
 }
 
 template <typename T>
