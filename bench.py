@@ -191,7 +191,7 @@ def roofline_nn(src, tgt, pk):
     peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     ach = flop / sec / 1e12
     executed = 6.0 * evals / sec / 1e12      # what the filter scan issues: 3 FFMA per evaluation (refine + fallback < 2 % more)
-    return {"kernel": "nn_scan_f32_kernel<16> + merge + exact fallback (one dicp_nn_scan_f32 call)", "bound": "fp32",
+    return {"kernel": "nn_scan_f32_kernel<8> + exact fallback (one dicp_nn_scan_f32 call)", "bound": "fp32",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms_per_launch": sec * 1e3,
             "executed_tflops": executed, "frac_executed": executed / peak,
             "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],

@@ -254,7 +254,7 @@ __device__ __forceinline__ float nn_filter_margin(float x0, float x1, float x2, 
 }
 
 template <int Q>
-__global__ void __launch_bounds__(NNF_THREADS, 1)
+__global__ void __launch_bounds__(NNF_THREADS, 4)
 nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n,
                    int m_pad, int tiles_per_split, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
                    float* __restrict__ part_d2, int32_t* __restrict__ part_idx, unsigned int* __restrict__ fb_count,
@@ -423,11 +423,9 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
   const int m_pad = nn_m_pad(m);
   int ctas_per_sm;
   if (elem_size == 4) {
-    // 16 queries per thread (2 CTAs / SM) once there is enough work for >= 4 waves of them, else 8 (4 CTAs / SM)
-    p.threads = NNF_THREADS; p.tile = NNF_TILE;
-    const long long ctas16 = (long long)N * ((n + NNF_THREADS * 16 - 1) / (NNF_THREADS * 16));
-    p.q = ctas16 >= 148LL * 2 * 4 ? 16 : 8;
-    ctas_per_sm = p.q == 16 ? 2 : 4;
+    // 8 queries per thread, 128 registers, 4 CTAs / SM (tools/nn_tune.cu: 8.75 ms at C3; 16 queries / 2 CTAs: 8.80 ms)
+    p.threads = NNF_THREADS; p.tile = NNF_TILE; p.q = 8;
+    ctas_per_sm = 4;
   } else {
     p.threads = NN_THREADS; p.tile = NN_TILE; p.q = 2; ctas_per_sm = 4;
   }
@@ -435,7 +433,7 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
   const int tiles_total = (m_pad + p.tile - 1) / p.tile;
   const long long base = (long long)p.gx * N;
   const long long slots = 148LL * ctas_per_sm;
-  const long long want = slots * 16;         // >= 16 waves => tail loss of a few percent at most
+  const long long want = slots * 6;          // >= 6 waves => the short last wave costs a few percent at most
   long long s = (want + base - 1) / base;
   const long long max_by_work = tiles_total / 8 > 0 ? tiles_total / 8 : 1;   // >= 8 tiles per CTA keeps prologue/refine overhead small
   const long long fill = (slots + base - 1) / base;                            // but always fill the machine
@@ -476,11 +474,7 @@ static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_
                        int n, int m_pad, int32_t* idx_out, float* d2_out, const int* stop_flag) {
   dim3 grid(p.gx, N, p.nsplit);
   DICP_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(unsigned int) * N, st));
-  if (p.q == 16)
-    nn_scan_f32_kernel<16><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
-                                                          w.part_idx, w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
-  else
-    nn_scan_f32_kernel<8><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
+  nn_scan_f32_kernel<8><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
                                                          w.part_idx, w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
   DICP_LAUNCH_CHECK();
   return 0;

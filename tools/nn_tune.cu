@@ -570,16 +570,15 @@ int main(int argc, char** argv) {
   cudaMalloc(&d_ps, (size_t)N * n * sizeof(float4));
   pack_kernel_s<<<dim3((n + 255) / 256, N), 256>>>(d_t, n, d_ps);
   cudaDeviceSynchronize();
-  run_s<8, 128, 1, 512, 0, 16>("scalar expanded Q8  ch16 tile512");
-  run_s<8, 128, 1, 512, 0, 32>("scalar expanded Q8  ch32 tile512");
-  run_s<8, 128, 1, 1024, 0, 32>("scalar expanded Q8  ch32 tile1024");
-  run_s<16, 128, 1, 512, 0, 16>("scalar expanded Q16 ch16 tile512");
-  run_s<16, 128, 1, 512, 0, 32>("scalar expanded Q16 ch32 tile512");
-  run_s<16, 128, 1, 1024, 0, 32>("scalar expanded Q16 ch32 tile1024");
-  run_s<16, 128, 1, 1024, 0, 64>("scalar expanded Q16 ch64 tile1024");
-  run_s<16, 64, 1, 512, 0, 32>("scalar expanded Q16 T64 ch32");
-  run_s<16, 256, 1, 512, 0, 32>("scalar expanded Q16 T256 ch32");
-  run_s<20, 128, 1, 512, 0, 32>("scalar expanded Q20 ch32");
-  run_s<24, 128, 1, 512, 0, 32>("scalar expanded Q24 ch32");
+  run_s<16, 128, 1, 512, 0, 32>("scalar expanded Q16 ch32 minb1");
+  run_s<16, 128, 3, 512, 0, 32>("scalar expanded Q16 ch32 minb3");
+  run_s<12, 128, 3, 512, 0, 32>("scalar expanded Q12 ch32 minb3");
+  run_s<12, 128, 4, 512, 0, 32>("scalar expanded Q12 ch32 minb4");
+  run_s<8, 128, 4, 512, 0, 32>("scalar expanded Q8  ch32 minb4");
+  run_s<8, 128, 5, 512, 0, 32>("scalar expanded Q8  ch32 minb5");
+  run_s<16, 96, 3, 512, 0, 32>("scalar expanded Q16 T96 ch32 minb3");
+  run_s<16, 64, 5, 512, 0, 32>("scalar expanded Q16 T64 ch32 minb5");
+  run_s<16, 64, 6, 512, 0, 32>("scalar expanded Q16 T64 ch32 minb6");
+  run_s<16, 160, 2, 512, 0, 32>("scalar expanded Q16 T160 ch32 minb2");
   return 0;
 }
