@@ -499,8 +499,12 @@ static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const f
   if (fs < 1) fs = 1;
   const int tps = (tiles_total + fs - 1) / fs;
   fs = (tiles_total + tps - 1) / tps;
-  int gx = (w.fb_cap + NN_FB_THREADS * NN_FB_Q - 1) / (NN_FB_THREADS * NN_FB_Q);
-  if (gx > 4) gx = 4;                        // CTAs stride over longer lists; empty CTAs are not free
+  // CTAs stride over the lists (their lengths are only known on the device).  Few CTAs per pair when
+  // there are many pairs (empty CTAs are not free), enough to fill the machine when there are few.
+  const int gx_cap = (w.fb_cap + NN_FB_THREADS * NN_FB_Q - 1) / (NN_FB_THREADS * NN_FB_Q);
+  int gx = (148 * 8 + N * fs - 1) / (N * fs);
+  if (gx < 4) gx = 4;
+  if (gx > gx_cap) gx = gx_cap;
   dim3 grid(gx, N, fs);
   nn_scan_kernel<float, NN_FB_Q, true, NN_FB_THREADS><<<grid, NN_FB_THREADS, 0, st>>>(q, state, packed, n, m_pad, tps, idx_out, d2_out, nullptr, nullptr,
                                                                                       w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);

@@ -336,3 +336,64 @@ def test_gn_accumulate_stage_vs_oracle():
         A = A + A.transpose(1, 2) - torch.diag_embed(torch.diagonal(A, dim1=1, dim2=2))
         assert rel_err(A, A_ref) < tol
         assert (red[:, 29] == n).all() and (red[:, 30] == n).all()
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json configs 2 and 4 (full sizes, size-independent properties + oracle on a subset)
+# ---------------------------------------------------------------------------------------
+def test_config2_pt2pt_64x4096_forward():
+    """configs[1]: batched point-to-point ICP, 64 pairs x 4096 points, forward only."""
+    from oracle.dicp_oracle import IcpSettings, icp_forward, make_wavy_pair
+    N, n, K = 64, 4096, 10
+    src, tgt = make_wavy_pair(N, n, n, seed=2000, dtype=torch.float32, with_normals=False)
+    icp = _icp("pt2pt", True, K, 1e-12, const_iter=True)
+    with torch.no_grad():
+        res = icp.icp(src.cuda(), tgt.cuda(), torch.eye(4, device="cuda").repeat(N, 1, 1), dim=3)
+    assert res["T"].shape == (N, 4, 4) and res["weights"].shape == (N, K, 3 * n, 1) and res["pc"].shape == (N, n, 3)
+    # batch == per-chunk loop (tests/test_ICP_inputs.py:106-107 at scale)
+    with torch.no_grad():
+        sub = icp.icp(src[5:9].cuda(), tgt[5:9].cuda(), torch.eye(4, device="cuda").repeat(4, 1, 1), dim=3)
+    assert torch.equal(sub["T"], res["T"][5:9])
+    # the generator moved the source by Rz(0.02), t=(0.3,-0.2,0.05): ICP must undo it
+    c, s = np.cos(0.02), np.sin(0.02)
+    Rz = torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
+    T_true = torch.eye(4)
+    T_true[:3, :3] = Rz.T
+    T_true[:3, 3] = -Rz.T @ torch.tensor([0.3, -0.2, 0.05])
+    assert (res["T"].cpu() - T_true).abs().max() < 5e-3
+    # oracle (fp32 torch CPU path of the reference) on 4 pairs
+    cfg = IcpSettings(icp_type="pt2pt", max_iterations=K, tolerance=1e-12, const_iter=True, dim=3)
+    ref = icp_forward(src[:4], tgt[:4], torch.eye(4).repeat(4, 1, 1), torch.ones((4, 3 * n)), cfg)
+    assert rel_err(res["T"][:4].cpu(), ref["T"]) < 1e-5
+
+
+def test_config4_lidar_130k_single_pair():
+    """configs[3]: one 130 000 x 130 000 pair, forward + backward (the reference cannot run it:
+    its distance matrix would be 67.6 GB).  The target range is split over the SMs."""
+    from dicp_b200 import _functions
+    from oracle.dicp_oracle import make_wavy_pair, nn_index_exact
+    n = 130000
+    src, tgt = make_wavy_pair(1, n, n, seed=4000, dtype=torch.float32, extent=60.0)
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    icp = _icp("pt2pl", True, 10, 1e-12, const_iter=True)
+    res = icp.icp(s, t, torch.eye(4, device="cuda").unsqueeze(0), trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+    res["T"].sum().backward()
+    assert torch.isfinite(res["T"]).all() and torch.isfinite(s.grad).all() and torch.isfinite(t.grad).all()
+    c, sn = np.cos(0.02), np.sin(0.02)
+    Rz = torch.tensor([[c, -sn, 0.0], [sn, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
+    T_true = torch.eye(4)
+    T_true[:3, :3] = Rz.T
+    T_true[:3, 3] = -Rz.T @ torch.tensor([0.3, -0.2, 0.05])
+    assert (res["T"][0].cpu() - T_true).abs().max() < 2e-3
+    assert (res["stats"]["iterations"] == 10).all()
+    # NN indices of the full-size search on a query subset vs the fp64-exact argmin
+    idx, d2 = _functions.nn_argmin(src.cuda(), t.detach(), return_d2=True)
+    pick = torch.arange(0, n, 61)[:2048]
+    ref, best, second = nn_index_exact(src[:, pick], tgt[:, :, :3])
+    tie_free = (second - best) > 8 * EPS32 * best
+    assert torch.equal(idx.cpu().long()[:, pick][tie_free], ref[tie_free])
+    # idempotence: transforming by the result and searching again changes almost no correspondence
+    idx2 = _functions.nn_argmin(res["pc"].detach(), t.detach())
+    idx3 = _functions.nn_argmin(res["pc"].detach().clone(), t.detach())
+    assert torch.equal(idx2, idx3)

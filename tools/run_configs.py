@@ -1,0 +1,51 @@
+"""Time BASELINE.json configs 2 (64 x 4096 pt2pt forward) and 4 (130k x 130k single pair fwd+bwd)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dICP.ICP import ICP  # noqa: E402
+from oracle.dicp_oracle import make_wavy_pair  # noqa: E402  (input generator only)
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+out = {}
+src, tgt = make_wavy_pair(64, 4096, 4096, seed=2000, dtype=torch.float32, with_normals=False)
+src, tgt, T0 = src.cuda(), tgt.cuda(), torch.eye(4, device="cuda").repeat(64, 1, 1)
+icp = ICP(icp_type="pt2pt", max_iterations=10, tolerance=1e-12)
+icp.const_iter = True
+with torch.no_grad():
+    ms = timed(lambda: icp.icp(src, tgt, T0, dim=3))
+out["config2_pt2pt_64x4096_fwd"] = {"ms": ms, "pairs_per_s": 64 / ms * 1e3}
+
+src, tgt = make_wavy_pair(1, 130000, 130000, seed=4000, dtype=torch.float32, extent=60.0)
+src, tgt, T0 = src.cuda().requires_grad_(True), tgt.cuda().requires_grad_(True), torch.eye(4, device="cuda").unsqueeze(0)
+icp = ICP(icp_type="pt2pl", max_iterations=10, tolerance=1e-12)
+icp.const_iter = True
+
+
+def step4():
+    src.grad = tgt.grad = None
+    res = icp.icp(src, tgt, T0, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+    res["T"].sum().backward()
+
+
+ms = timed(step4, reps=3, warm=1)
+out["config4_pt2pl_1x130k_fwd_bwd"] = {"ms": ms, "pairs_per_s": 1 / ms * 1e3,
+                                       "nn_tflops_algorithmic": 8.0 * 130000.0 ** 2 * 10 / (ms * 1e-3) / 1e12}
+print(json.dumps(out))
