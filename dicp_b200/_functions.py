@@ -67,6 +67,41 @@ class GatherRows(torch.autograd.Function):
         return gy, None
 
 
+class KabschSums(torch.autograd.Function):
+    """sums[b] = (sum p, sum q, sum q p^T) over the correspondences q_i = y[b, idx[b,i], :3]
+    (ICP.py:557-563 without the O(1) 3x3 part).  x (N,n,3), y (N,m,S), idx (N,n) int32 -> (N,16)."""
+
+    @staticmethod
+    def forward(ctx, x, y, idx):
+        lib = load_library()
+        x, y = x.contiguous(), y.contiguous()
+        N, n, _ = x.shape
+        m, S = y.shape[1], y.shape[2]
+        sfx = suffix(x.dtype)
+        sums = torch.empty((N, 16), dtype=x.dtype, device=x.device)
+        ws = _workspace(lib.dicp_kabsch_workspace_bytes(N, n), x.device)
+        with torch.cuda.device(x.device):
+            rc = getattr(lib, "dicp_kabsch_sums_" + sfx)(ptr(x), ptr(y), ptr(idx), N, n, m, S, ptr(sums), ptr(ws), ws.numel(),
+                                                         stream_ptr(x.device))
+        check(rc, "dicp_kabsch_sums_" + sfx)
+        ctx.save_for_backward(x, y, idx)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = load_library()
+        x, y, idx = ctx.saved_tensors
+        N, n, _ = x.shape
+        m, S = y.shape[1], y.shape[2]
+        sfx = suffix(x.dtype)
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        with torch.cuda.device(x.device):
+            rc = getattr(lib, "dicp_kabsch_sums_bwd_" + sfx)(ptr(x), ptr(y), ptr(idx), N, n, m, S, ptr(g.contiguous()), ptr(gx), ptr(gy),
+                                                             stream_ptr(x.device))
+        check(rc, "dicp_kabsch_sums_bwd_" + sfx)
+        return gx, gy, None
+
+
 def make_params(icp_type, dim, differentiable, loss_name, loss_metric, trim_dist, tanh_steepness, tolerance,
                 max_iterations, const_iter, match_ratio_thresh, check_every=1):
     if loss_name not in _lib.LOSS_IDS:

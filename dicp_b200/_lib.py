@@ -37,6 +37,7 @@ _SIGNATURES = {
     "dicp_nn_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_nn_packed_bytes": ([_I, _I, _I], _Z),
+    "dicp_kabsch_workspace_bytes": ([_I, _I], _Z),
 }
 for _s in ("f32", "f64"):
     _SIGNATURES["dicp_nn_argmin_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
@@ -49,6 +50,8 @@ for _s in ("f32", "f64"):
                                              ctypes.POINTER(ctypes.c_int32), _P, _Z, _P], _I)
     _SIGNATURES["dicp_icp_backward_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams), _I,
                                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P], _I)
+    _SIGNATURES["dicp_kabsch_sums_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P], _I)
+    _SIGNATURES["dicp_kabsch_sums_bwd_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I)
     _SIGNATURES["dicp_gn_accumulate_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams),
                                                _P, _P, _P, _Z, _P], _I)
 

@@ -161,6 +161,22 @@ DICP_API int dicp_gn_accumulate_f64(const double* source, const double* target, 
                            const double* C_r, int N, int n, int m, int S, const dicp_params* params,
                            double* weights_out, double* red_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Kabsch / SVD point-to-point step: the per-point half of dICP/ICP.py:557-563 ----------
+ * sums[b] = ( sum_i p_i (3), sum_i q_i (3), sum_i q_i p_i^T (9, row-major), pad ),  q_i = tgt[b, idx[b,i], :3]
+ * from which the centroids and the cross-covariance W = M/n - q_mean p_mean^T follow; the 3x3
+ * SVD, determinant fix and composition (ICP.py:566-578) are O(1) per pair and stay on the host
+ * side (torch).  The _bwd entry is the adjoint used by autograd: grad_source is overwritten,
+ * grad_target is zeroed and scatter-added into.                                              */
+DICP_API size_t dicp_kabsch_workspace_bytes(int N, int n);
+DICP_API int dicp_kabsch_sums_f32(const float* source, const float* target, const int32_t* idx, int N, int n, int m, int S,
+                         float* sums /*[N,16]*/, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_kabsch_sums_f64(const double* source, const double* target, const int32_t* idx, int N, int n, int m, int S,
+                         double* sums /*[N,16]*/, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_kabsch_sums_bwd_f32(const float* source, const float* target, const int32_t* idx, int N, int n, int m, int S,
+                             const float* grad_sums, float* grad_source, float* grad_target, void* stream);
+DICP_API int dicp_kabsch_sums_bwd_f64(const double* source, const double* target, const int32_t* idx, int N, int n, int m, int S,
+                             const double* grad_sums, double* grad_source, double* grad_target, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

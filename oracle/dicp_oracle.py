@@ -35,6 +35,7 @@ __all__ = [
     "trim_weight",
     "robust_weight",
     "icp_forward",
+    "kabsch_icp",
     "make_wavy_pair",
 ]
 
@@ -301,6 +302,46 @@ def icp_forward(source: torch.Tensor, target: torch.Tensor, T_init: torch.Tensor
         "stats": {"converged": converged, "iterations": num_iters, "matched_ratio": match_ratio},
         "iters_run": k_run,
     }
+
+
+# --------------------------------------------------------------------------------------
+# Kabsch / SVD point-to-point ICP  (ICP.py:533-591, "not yet integrated" upstream)
+# --------------------------------------------------------------------------------------
+def kabsch_icp(source: torch.Tensor, target: torch.Tensor, T_init: torch.Tensor, max_iterations: int,
+               tolerance: float, literal: bool = False):
+    """Single pair: source (n,>=3), target (m,>=3), T_init (4,4) -> (moved source (n,3), T (4,4), iterations).
+
+    Restates ICP.py:545-591 step by step.  Two quirks of the reference are kept: T_init is only
+    composed into the returned transform, it is NOT applied to the source before the first search
+    (ICP.py:545-547), and convergence compares the moved points with the neighbours found before
+    the move (ICP.py:585).  One is NOT kept unless `literal=True`: ICP.py:566-570 names the third
+    output of `torch.svd` "Vt" although it is V, and forms U diag(1,1,det) V; that equals the
+    Kabsch rotation U diag(1,1,det) V^T only when V happens to be symmetric (it is on the planar
+    test fixture, where the reference reaches its known answer; on a general 3-D cloud it does
+    not).  The default here is the Kabsch rotation."""
+    ps = source[:, 0:3]
+    tgt = target[:, 0:3]
+    T = T_init
+    n = ps.shape[0]
+    it = 0
+    for it in range(1, max_iterations + 1):
+        idx = nn_index_reference(ps.detach()[None], tgt.detach()[None])[0]            # ICP.py:553-555 (per-point loop)
+        nn_t = tgt[idx]
+        p_mean = ps.mean(dim=0).reshape(3, 1)                                          # ICP.py:558
+        q_mean = nn_t.mean(dim=0).reshape(3, 1)                                        # ICP.py:559
+        W = (nn_t.T - q_mean) @ (ps.T - p_mean).T / n                                  # ICP.py:562-563
+        U, _, V = torch.svd(W)                                                         # ICP.py:566
+        d = torch.det(U) * torch.det(V)
+        D = torch.diag(torch.stack((torch.ones_like(d), torch.ones_like(d), d)))
+        C = U @ D @ (V if literal else V.T)                                            # ICP.py:570
+        r = q_mean - C @ p_mean                                                        # ICP.py:573
+        T_up = torch.eye(4, dtype=ps.dtype)
+        T_up = torch.cat((torch.cat((C, r), dim=1), T_up[3:4]), dim=0)                 # ICP.py:577
+        T = T_up @ T                                                                   # ICP.py:578
+        ps = (C @ ps.T + r).T                                                          # ICP.py:581
+        if float(torch.sum((ps - nn_t).detach() ** 2)) < tolerance:                           # ICP.py:585
+            break
+    return ps, T, it
 
 
 # --------------------------------------------------------------------------------------

@@ -282,6 +282,19 @@ def loss_cases():
     save("loss_known_answers", **out)
 
 
+def svd_case():
+    """ICP.py:533-591 on the planar fixture (hard NN).  The reference reaches its known answer here."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    icp = ICP(icp_type="pt2pt", max_iterations=50, tolerance=1e-20)
+    icp.nn.use_gumbel = False
+    src = torch.tensor(scan[:, :3])
+    tgt = torch.tensor(cmap[:, :3])
+    ps, T = icp.pt2pt_dICP_SVD(src, tgt, torch.eye(4, dtype=src.dtype))
+    save("svd_fixture", source=npy(src), target=npy(tgt), pc=npy(ps), T=npy(T))
+
+
 nn_cases()
 loss_cases()
+svd_case()
 print("done")

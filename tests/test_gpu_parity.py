@@ -397,3 +397,53 @@ def test_config4_lidar_130k_single_pair():
     idx2 = _functions.nn_argmin(res["pc"].detach(), t.detach())
     idx3 = _functions.nn_argmin(res["pc"].detach().clone(), t.detach())
     assert torch.equal(idx2, idx3)
+
+
+# ---------------------------------------------------------------------------------------
+# Kabsch / SVD point-to-point path (ICP.py:533-591)
+# ---------------------------------------------------------------------------------------
+def test_kabsch_fixture_matches_reference_and_known_answer():
+    from dICP.ICP import ICP
+    g = load_golden("svd_fixture")
+    icp = ICP(icp_type="pt2pt", max_iterations=50, tolerance=1e-20)
+    src, tgt = tt(g["source"]).cuda(), tt(g["target"]).cuda()
+    ps, T = icp.pt2pt_dICP_SVD(src, tgt, torch.eye(4, dtype=src.dtype, device="cuda"))
+    assert ps.shape == (65, 3) and T.shape == (4, 4)
+    assert rel_err(T.cpu(), g["T"]) < 1e-10 and rel_err(ps.cpu(), g["pc"]) < 1e-10
+    assert np.linalg.norm(se3_log(T_ts_true() @ np.linalg.inv(T.cpu().numpy()))) < 1e-10
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-5)])
+def test_kabsch_3d_vs_oracle_with_gradients(dtype, tol):
+    from dICP.ICP import ICP
+    from oracle.dicp_oracle import kabsch_icp, make_wavy_pair
+    src, tgt = make_wavy_pair(2, 900, 1100, seed=31, dtype=torch.float64, with_normals=False, noise=0.01)
+    src, tgt = src.to(dtype), tgt.to(dtype)
+    icp = ICP(icp_type="pt2pt", max_iterations=6, tolerance=0.0)
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    T0 = torch.eye(4, dtype=dtype, device="cuda").repeat(2, 1, 1)
+    ps, T = icp.pt2pt_dICP_SVD(s, t, T0)
+    wT = torch.arange(1, 13, dtype=dtype, device="cuda").reshape(3, 4)
+    ((T[:, :3, :] * wT).sum() + 0.01 * ps.sum()).backward()
+    for b in range(2):
+        sr = src[b].double().requires_grad_(True)
+        tr = tgt[b].double().requires_grad_(True)
+        ps_r, T_r, it = kabsch_icp(sr, tr, torch.eye(4, dtype=torch.float64), 6, 0.0)
+        ((T_r[:3, :] * wT.cpu().double()).sum() + 0.01 * ps_r.sum()).backward()
+        assert rel_err(T[b].detach().cpu(), T_r.detach()) < tol
+        assert rel_err(ps[b].detach().cpu(), ps_r.detach()) < tol
+        assert rel_err(s.grad[b].cpu(), sr.grad) < 50 * tol
+        assert rel_err(t.grad[b].cpu(), tr.grad) < 50 * tol
+
+
+def test_kabsch_sums_stage_vs_torch():
+    from dicp_b200 import _functions
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn((3, 5000, 3), generator=gen, dtype=torch.float64).cuda()
+    y = torch.randn((3, 777, 6), generator=gen, dtype=torch.float64).cuda()
+    idx = torch.randint(0, 777, (3, 5000), generator=gen, dtype=torch.int32).cuda()
+    sums = _functions.KabschSums.apply(x, y, idx)
+    q = torch.gather(y[:, :, :3], 1, idx.long().unsqueeze(-1).expand(-1, -1, 3))
+    ref = torch.cat((x.sum(1), q.sum(1), (q.transpose(1, 2) @ x).reshape(3, 9)), dim=1)
+    assert rel_err(sums[:, :15].cpu(), ref.cpu()) < 1e-13

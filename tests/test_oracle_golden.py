@@ -172,3 +172,32 @@ def test_loss_known_answers():
             assert np.allclose(robust_weight("huber", e, 1.3, diff).numpy(), g["huber_%d_%s" % (diff, key)], rtol=1e-14)
             assert np.allclose(robust_weight("cauchy", e, 0.7, diff).numpy(), g["cauchy_%d_%s" % (diff, key)], rtol=1e-14)
             assert np.allclose(trim_weight(e, 1.9, diff, 5.0).numpy(), g["trim_%d_%s" % (diff, key)], rtol=1e-14)
+
+
+def test_kabsch_fixture_golden_and_known_answer():
+    """ICP.py:533-591: the literal restatement reproduces the reference on its planar fixture, and
+    the Kabsch-correct variant reaches the same known answer (tests/test_ICP.py:45-47)."""
+    from oracle.dicp_oracle import kabsch_icp
+    g = load_golden("svd_fixture")
+    src, tgt = tt(g["source"]), tt(g["target"])
+    ps, T, _ = kabsch_icp(src, tgt, torch.eye(4, dtype=src.dtype), 50, 1e-20, literal=True)
+    assert rel_err(T, g["T"]) < 1e-12 and rel_err(ps, g["pc"]) < 1e-12
+    ps2, T2, _ = kabsch_icp(src, tgt, torch.eye(4, dtype=src.dtype), 50, 1e-20)
+    assert np.linalg.norm(se3_log(T_ts_true() @ np.linalg.inv(T2.numpy()))) < 1e-10
+    assert rel_err(T2, g["T"]) < 1e-10
+
+
+def test_kabsch_oracle_recovers_3d_motion():
+    """On a general 3-D cloud only the Kabsch rotation U diag V^T recovers the motion."""
+    from oracle.dicp_oracle import kabsch_icp
+    gen = torch.Generator().manual_seed(0)
+    P = torch.randn((300, 3), generator=gen, dtype=torch.float64) * 3
+    a, b = 0.03, 0.02
+    Rz = torch.tensor([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], dtype=torch.float64)
+    Rx = torch.tensor([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]], dtype=torch.float64)
+    R, t = Rz @ Rx, torch.tensor([0.05, -0.02, 0.03], dtype=torch.float64)
+    Q = P @ R.T + t
+    ps, T, it = kabsch_icp(P, Q, torch.eye(4, dtype=torch.float64), 30, 1e-24)
+    assert (T[:3, :3] - R).abs().max() < 1e-10 and (T[:3, 3] - t).abs().max() < 1e-10
+    _, T_lit, _ = kabsch_icp(P, Q, torch.eye(4, dtype=torch.float64), 30, 1e-24, literal=True)
+    assert (T_lit[:3, :3] - R).abs().max() > 1e-3
