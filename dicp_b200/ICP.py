@@ -47,6 +47,10 @@ class ICP:
         self.check_every = 1
         # not in the reference: CUDA device used when the inputs live on the CPU
         self.device = None
+        # not in the reference: 'brute' = tiled brute-force scan (default), 'grid' = exact search through a
+        # uniform grid built once per call (same correspondences, O(n) per iteration); optional YAML key
+        # dICP.functionality.nn_search
+        self.nn_search = func.get('nn_search', 'brute')
 
     def icp(self, source, target, T_init, weight=None, trim_dist=None, loss_fn=None, dim=3):
         return self.dICP(source, target, T_init, weight, trim_dist, loss_fn, dim)
@@ -90,7 +94,7 @@ class ICP:
         params = _functions.make_params(
             self.icp_type, dim, self.diff, loss_name, loss_metric, trim_dist,
             self.config['dICP']['parameters']['tanh_steepness'], self.tolerance, self.max_iterations,
-            self.const_iter, self.match_ratio_thresh, self.check_every)
+            self.const_iter, self.match_ratio_thresh, self.check_every, self.nn_search)
 
         pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
             source.to(dev), target.to(dev), T_init.to(dev), w_point.to(dev), params)

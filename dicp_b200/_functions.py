@@ -14,8 +14,9 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def nn_argmin(x, y, return_d2=False):
-    """x (N,n,3), y (N,m,3|6) CUDA tensors -> idx (N,n) int32 [, d2 (N,n)] (nn.py:32-35)."""
+def nn_argmin(x, y, return_d2=False, search="brute"):
+    """x (N,n,3), y (N,m,3|6) CUDA tensors -> idx (N,n) int32 [, d2 (N,n)] (nn.py:32-35).
+    search: 'brute' (tiled scan) or 'grid' (uniform grid, same result)."""
     require_cuda()
     lib = load_library()
     assert x.is_cuda and y.is_cuda and x.dtype == y.dtype
@@ -26,11 +27,15 @@ def nn_argmin(x, y, return_d2=False):
     sfx = suffix(x.dtype)
     idx = torch.empty((N, n), dtype=torch.int32, device=x.device)
     d2 = torch.empty((N, n), dtype=x.dtype, device=x.device) if return_d2 else None
-    ws = _workspace(lib.dicp_nn_workspace_bytes(N, n, m, x.element_size()), x.device)
+    if search == "grid":
+        name = "dicp_nn_argmin_grid_" + sfx
+        ws = _workspace(lib.dicp_nn_grid_workspace_bytes(N, m, x.element_size()), x.device)
+    else:
+        name = "dicp_nn_argmin_" + sfx
+        ws = _workspace(lib.dicp_nn_workspace_bytes(N, n, m, x.element_size()), x.device)
     with torch.cuda.device(x.device):
-        rc = getattr(lib, "dicp_nn_argmin_" + sfx)(ptr(x), ptr(y), N, n, m, S, ptr(idx), ptr(d2), ptr(ws), ws.numel(),
-                                                   stream_ptr(x.device))
-    check(rc, "dicp_nn_argmin_" + sfx)
+        rc = getattr(lib, name)(ptr(x), ptr(y), N, n, m, S, ptr(idx), ptr(d2), ptr(ws), ws.numel(), stream_ptr(x.device))
+    check(rc, name)
     return (idx, d2) if return_d2 else idx
 
 
@@ -103,7 +108,7 @@ class KabschSums(torch.autograd.Function):
 
 
 def make_params(icp_type, dim, differentiable, loss_name, loss_metric, trim_dist, tanh_steepness, tolerance,
-                max_iterations, const_iter, match_ratio_thresh, check_every=1):
+                max_iterations, const_iter, match_ratio_thresh, check_every=1, nn_search="brute"):
     if loss_name not in _lib.LOSS_IDS:
         raise ValueError("Invalid loss name: {}".format(loss_name))          # loss.py:19
     p = DicpParams()
@@ -116,6 +121,9 @@ def make_params(icp_type, dim, differentiable, loss_name, loss_metric, trim_dist
     p.max_iterations = int(max_iterations)
     p.const_iter = int(bool(const_iter))
     p.check_every = int(check_every)
+    if nn_search not in _lib.NN_MODES:
+        raise ValueError("nn_search must be 'brute' or 'grid', got {!r}".format(nn_search))
+    p.nn_mode = _lib.NN_MODES[nn_search]
     p.loss_metric = float(loss_metric) if loss_name is not None else 1.0
     p.trim_dist = float(trim_dist) if use_trim else 0.0
     p.tanh_steepness = float(tanh_steepness)

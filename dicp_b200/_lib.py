@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdicp_b200.so")
 
 DICP_PT2PL, DICP_PT2PT = 0, 1
 LOSS_IDS = {None: 0, "huber": 1, "cauchy": 2}
+NN_MODES = {"brute": 0, "grid": 1}
 STATE_STRIDE = 64
 
 
@@ -21,7 +22,7 @@ class DicpParams(ctypes.Structure):
     _fields_ = [
         ("icp_type", ctypes.c_int32), ("dim", ctypes.c_int32), ("differentiable", ctypes.c_int32),
         ("loss_id", ctypes.c_int32), ("use_trim", ctypes.c_int32), ("max_iterations", ctypes.c_int32),
-        ("const_iter", ctypes.c_int32), ("check_every", ctypes.c_int32),
+        ("const_iter", ctypes.c_int32), ("check_every", ctypes.c_int32), ("nn_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("loss_metric", ctypes.c_double), ("trim_dist", ctypes.c_double), ("tanh_steepness", ctypes.c_double),
         ("tolerance", ctypes.c_double), ("match_ratio_thresh", ctypes.c_double),
     ]
@@ -38,9 +39,11 @@ _SIGNATURES = {
     "dicp_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_nn_packed_bytes": ([_I, _I, _I], _Z),
     "dicp_kabsch_workspace_bytes": ([_I, _I], _Z),
+    "dicp_nn_grid_workspace_bytes": ([_I, _I, _I], _Z),
 }
 for _s in ("f32", "f64"):
     _SIGNATURES["dicp_nn_argmin_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
+    _SIGNATURES["dicp_nn_argmin_grid_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_nn_pack_" + _s] = ([_P, _I, _I, _I, _P, _P], _I)
     _SIGNATURES["dicp_nn_scan_" + _s] = ([_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_gather_rows_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)

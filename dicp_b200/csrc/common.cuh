@@ -96,6 +96,24 @@ int nn_search(const T* q, const double* state, const typename Vec4<T>::type* pac
               int32_t* idx_out, T* d2_out, const int* stop_flag, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t nn_search_ws_bytes(int N, int n, int m, int elem_size);
 
+// ---- uniform-grid exact NN (grid_nn_kernels.cu) ---------------------------------------
+struct GridWorkspace {
+  double* gparams;      // [N, 8]  origin xyz, h, 1/h
+  int* gdims;           // [N, 4]  nx, ny, nz, ncells
+  int* cell_start;      // [N, cells_stride]
+  int* cell_count;      // [N, cells_stride]  histogram, then scatter cursor
+  int* cell_of;         // [N, m]
+  void* recs;           // [N, m] GridRec<T>
+  int* max_occupancy;   // [1]
+  int cells_stride;
+  size_t total;
+};
+GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int m, int elem_size);
+template <typename T> int grid_build(const T* tgt, int N, int m, int S, const GridWorkspace& g, cudaStream_t st);
+template <typename T>
+int grid_search(const T* q, const double* state, int N, int n, int m, const GridWorkspace& g, int32_t* idx_out, T* d2_out,
+                const int* stop_flag, cudaStream_t st);
+
 // ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------
 int gn_blocks_per_pair(int n);
 template <typename T>
@@ -116,6 +134,8 @@ struct IcpWorkspace {
   Ctrl* ctrl;
   double* bw_state;    // [N, BW_STRIDE]
   double* bw_partials; // [N, nblk, BW_NRED]
+  void* grid_ws;       // uniform-grid index of the targets (nn_mode == DICP_NN_GRID)
+  size_t grid_ws_bytes;
   size_t total;
 };
 IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size);

@@ -274,6 +274,8 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
   w.ctrl = ar.take<Ctrl>(1);
   w.bw_state = ar.take<double>((size_t)N * BW_STRIDE);
   w.bw_partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * BW_NRED);
+  w.grid_ws_bytes = grid_ws_layout(nullptr, 0, N, m, elem_size).total;
+  w.grid_ws = ar.take<char>(w.grid_ws_bytes);
   w.total = ar.off;
   return w;
 }
@@ -292,6 +294,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   DICP_CHECK_ARG(S == 3 || S == 6, "target must have 3 or 6 columns");
   DICP_CHECK_ARG(p->loss_id >= 0 && p->loss_id <= 2, "invalid loss id");                 // loss.py:19
   DICP_CHECK_ARG(p->max_iterations >= 1, "max_iterations must be >= 1");
+  DICP_CHECK_ARG(p->nn_mode == DICP_NN_BRUTE || p->nn_mode == DICP_NN_GRID, "invalid nn_mode");
   if (ws == nullptr || ws_bytes < plan_workspace(nullptr, 0, N, n, m, sizeof(T)).total) {
     set_error("dicp_icp_forward: workspace too small");
     return DICP_ERR_WORKSPACE;
@@ -312,12 +315,28 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   int rc = nn_pack_targets<T>(target, N, m, S, (V4*)w.packed, st);
   if (rc) return rc;
 
+  // optional spatial index of the (static) targets; a cloud so clustered that one cell holds a
+  // large share of it (e.g. the 1000 x max(source) padding rows of a ragged batch stretch the
+  // bounding box) would make the ring search degenerate, so such calls keep the tiled scan
+  bool use_grid = p->nn_mode == DICP_NN_GRID;
+  GridWorkspace gw;
+  if (use_grid) {
+    gw = grid_ws_layout(w.grid_ws, w.grid_ws_bytes, N, m, sizeof(T));
+    rc = grid_build<T>(target, N, m, S, gw, st);
+    if (rc) return rc;
+    int max_occ = 0;
+    DICP_CUDA(cudaMemcpyAsync(&max_occ, gw.max_occupancy, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DICP_CUDA(cudaStreamSynchronize(st));
+    if (max_occ > 64 && max_occ > m / 64) use_grid = false;
+  }
+
   Ctrl h;
   memset(&h, 0, sizeof(h));
   for (int k = 0; k < K; ++k) {
     double* rec_k = saved_state + (size_t)k * rec_stride;
     int32_t* idx_k = saved_idx + (size_t)k * N * n;
-    rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st);
+    if (use_grid) rc = grid_search<T>(source, rec_k, N, n, m, gw, idx_k, nullptr, &w.ctrl->stop, st);
+    else rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st);
     if (rc) return rc;
     rc = gn_accumulate<T>(source, target, w_init, idx_k, rec_k, N, n, m, S, p,
                           weights != nullptr ? weights + (size_t)k * nw : nullptr, (long long)K * nw, w.partials, &w.ctrl->stop, st);

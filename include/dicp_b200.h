@@ -43,6 +43,11 @@ extern "C" {
 #define DICP_PT2PL 0            /* icp_type 'pt2pl' (ICP.py:143-146, 172-176) */
 #define DICP_PT2PT 1            /* icp_type 'pt2pt' (ICP.py:147-149, 177-180) */
 
+#define DICP_NN_BRUTE 0         /* tiled brute-force scan (the default; nn.py:32-35 semantics)          */
+#define DICP_NN_GRID  1         /* exact search through a per-pair uniform grid built once per call;
+                                   same result as the scan, O(n) instead of O(n m) per iteration;
+                                   falls back to the scan when a cloud is too clustered for a grid     */
+
 #define DICP_LOSS_NONE   0      /* loss_fn=None            (ICP.py:157-158) */
 #define DICP_LOSS_HUBER  1      /* loss.py:21-32 */
 #define DICP_LOSS_CAUCHY 2      /* loss.py:34-41 */
@@ -61,6 +66,8 @@ typedef struct dicp_params {
   int32_t const_iter;        /* yaml parameters.const_iter           ICP.py:33   */
   int32_t check_every;       /* host polls the device "all converged" flag every this
                                 many iterations when !const_iter (>=1; 1 == reference) */
+  int32_t nn_mode;           /* DICP_NN_BRUTE | DICP_NN_GRID (not in the reference)         */
+  int32_t reserved;          /* keep the doubles 8-byte aligned                              */
   double loss_metric;        /* loss_fn['metric']                    ICP.py:159  */
   double trim_dist;          /*                                      ICP.py:154  */
   double tanh_steepness;     /* yaml parameters.tanh_steepness       ICP.py:119  */
@@ -85,6 +92,14 @@ DICP_API int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, 
                        int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
 DICP_API int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, int S,
                        int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Same result through a uniform grid: build (bounding box, counting sort)
+ * + one-thread-per-query ring search.  ws sized by dicp_nn_grid_workspace_bytes.             */
+DICP_API size_t dicp_nn_grid_workspace_bytes(int N, int m, int elem_size);
+DICP_API int dicp_nn_argmin_grid_f32(const float* q, const float* tgt, int N, int n, int m, int S,
+                            int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, int n, int m, int S,
+                            int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
 
 /* The two stages of dicp_nn_argmin_*, exported for profiling and for callers that search the
  * same targets repeatedly (the solver loop packs once per call): pack the targets into

@@ -13,13 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emul", "emul.cpp")
 LIB = os.path.join(HERE, "host_emul", "libdicp_emul.so")
 HDR = os.path.join(HERE, "..", "dicp_b200", "csrc", "dicp_math.cuh")
+ABI = os.path.join(HERE, "..", "include", "dicp_b200.h")
 _lib = None
 
 
 def load():
     global _lib
     if _lib is None:
-        stale = (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR))
+        stale = (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(ABI))
         if stale:
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++", SRC, "-o", LIB])
         _lib = ctypes.CDLL(LIB)

@@ -447,3 +447,71 @@ def test_kabsch_sums_stage_vs_torch():
     q = torch.gather(y[:, :, :3], 1, idx.long().unsqueeze(-1).expand(-1, -1, 3))
     ref = torch.cat((x.sum(1), q.sum(1), (q.transpose(1, 2) @ x).reshape(3, 9)), dim=1)
     assert rel_err(sums[:, :15].cpu(), ref.cpu()) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------
+# uniform-grid exact NN: must return exactly what the brute-force scan returns
+# ---------------------------------------------------------------------------------------
+def _grid_equals_brute(x, y):
+    from dicp_b200._functions import nn_argmin
+    ib, db = nn_argmin(x.cuda(), y.cuda(), return_d2=True)
+    ig, dg = nn_argmin(x.cuda(), y.cuda(), return_d2=True, search="grid")
+    assert torch.equal(ib, ig), "grid and brute-force correspondences differ at %d queries" % int((ib != ig).sum())
+    assert torch.equal(db, dg)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 50, 3), (3, 700, 65), (2, 3000, 5000), (4, 16384, 16384)])
+def test_grid_nn_equals_brute_random(shape, dtype):
+    N, n, m = shape
+    if dtype == torch.float64 and n * m > 2e7:
+        pytest.skip("fp64 brute force at this size is slow")
+    gen = torch.Generator().manual_seed(n + 3 * m)
+    y = (torch.rand((N, m, 6), generator=gen, dtype=torch.float64) * 40 - 20).to(dtype)
+    x = (torch.rand((N, n, 3), generator=gen, dtype=torch.float64) * 44 - 22).to(dtype)      # some queries outside the box
+    _grid_equals_brute(x, y)
+
+
+def test_grid_nn_equals_brute_surface_duplicates_outliers():
+    from oracle.dicp_oracle import make_wavy_pair
+    src, tgt = make_wavy_pair(3, 8000, 9000, seed=77, dtype=torch.float32)
+    _grid_equals_brute(src, tgt)                                   # 2.5-D surface (most cells of the box empty)
+    dup = torch.cat((tgt, tgt[:, :100]), dim=1)                    # exact duplicates: lowest index must win
+    _grid_equals_brute(src, dup)
+    far = src.clone()
+    far[:, :7] += 500.0                                            # queries far outside the grid
+    _grid_equals_brute(far, tgt)
+    flat = tgt.clone()
+    flat[:, :, 2] = 0.0                                            # planar target (zero z extent)
+    _grid_equals_brute(src, flat)
+    line = tgt.clone()
+    line[:, :, 1:3] = 0.0                                          # collinear target
+    _grid_equals_brute(src, line)
+
+
+def test_icp_grid_mode_equals_brute_mode():
+    """The whole solver with nn_search='grid' reproduces nn_search='brute' bit for bit (same
+    correspondences, same kernels downstream), including a clustered cloud that makes the driver
+    keep the scan."""
+    from oracle.dicp_oracle import make_wavy_pair
+    src, tgt = make_wavy_pair(3, 4096, 5000, seed=91, dtype=torch.float32)
+    T0 = torch.eye(4, device="cuda").repeat(3, 1, 1)
+    outs = {}
+    for mode in ("brute", "grid"):
+        icp = _icp("pt2pl", True, 8, 1e-12, const_iter=True)
+        icp.nn_search = mode
+        s, t = src.cuda().requires_grad_(True), tgt.cuda().requires_grad_(True)
+        res = icp.icp(s, t, T0, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+        res["T"].sum().backward()
+        outs[mode] = (res["T"].detach(), res["weights"], s.grad.clone())
+    assert torch.equal(outs["brute"][0], outs["grid"][0]) and torch.equal(outs["brute"][1], outs["grid"][1])
+    assert torch.allclose(outs["brute"][2], outs["grid"][2], rtol=0, atol=0)
+    # ragged list batch: the padding rows (1000 x max) stretch the box -> scan fallback, same answer as golden
+    g = load_golden("ragged_pt2pl")
+    sl = [tt(g["s1"]).cuda(), tt(g["s2"]).cuda(), tt(g["s3"]).cuda()]
+    tl = [tt(g[k]).cuda() for k in ("t1", "t2", "t3")]
+    icp = _icp("pt2pl", True, 25, 1e-8)
+    icp.nn_search = "grid"
+    res = icp.icp(sl, tl, torch.eye(4, dtype=torch.float64, device="cuda").repeat(3, 1, 1), trim_dist=5.0,
+                  loss_fn={"name": "huber", "metric": 1.0}, dim=2)
+    _check(res, g, 1e-9)
