@@ -305,6 +305,11 @@ def run_ours(args):
     sec_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
     steps_e2e = max(2, args.steps // 2)
     pairs_total = PAIRS_PER_GPU * world
+    # the same workload with the exact uniform-grid search (identical correspondences)
+    icp.nn_search = "grid"
+    sec_grid, _ = timed(step_resident, args.steps, args.warmup)
+    sec_grid_e2e, _ = timed(step_e2e, steps_e2e, 1)
+    icp.nn_search = "brute"
 
     line = None
     if rank == 0:
@@ -345,6 +350,11 @@ def run_ours(args):
             "e2e": {"value": pairs_total * steps_e2e / sec_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * sec_e2e / steps_e2e, "api": "dICP.ICP.ICP.icp with pinned host tensors"},
             "gpu_launches": launches_per_step * args.steps,
+            "nn_search": "brute (tiled brute-force scan, the north-star kernel)",
+            "alt_nn_grid": {"value": pairs_total * args.steps / sec_grid, "unit": "pairs/s", "ms_per_step": 1e3 * sec_grid / args.steps,
+                            "e2e": pairs_total * steps_e2e / sec_grid_e2e,
+                            "note": "same workload with ICP.nn_search='grid': exact uniform-grid NN built once per call, "
+                                    "bit-identical correspondences (tests/test_gpu_parity.py::test_icp_grid_mode_equals_brute_mode)"},
             "roofline": roof, "roofline_gn": roof_gn, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -29,7 +29,7 @@ def nn_argmin(x, y, return_d2=False, search="brute"):
     d2 = torch.empty((N, n), dtype=x.dtype, device=x.device) if return_d2 else None
     if search == "grid":
         name = "dicp_nn_argmin_grid_" + sfx
-        ws = _workspace(lib.dicp_nn_grid_workspace_bytes(N, m, x.element_size()), x.device)
+        ws = _workspace(lib.dicp_nn_grid_workspace_bytes(N, n, m, x.element_size()), x.device)
     else:
         name = "dicp_nn_argmin_" + sfx
         ws = _workspace(lib.dicp_nn_workspace_bytes(N, n, m, x.element_size()), x.device)

@@ -39,7 +39,7 @@ _SIGNATURES = {
     "dicp_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_nn_packed_bytes": ([_I, _I, _I], _Z),
     "dicp_kabsch_workspace_bytes": ([_I, _I], _Z),
-    "dicp_nn_grid_workspace_bytes": ([_I, _I, _I], _Z),
+    "dicp_nn_grid_workspace_bytes": ([_I, _I, _I, _I], _Z),
 }
 for _s in ("f32", "f64"):
     _SIGNATURES["dicp_nn_argmin_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)

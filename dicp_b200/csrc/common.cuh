@@ -104,14 +104,18 @@ struct GridWorkspace {
   int* cell_count;      // [N, cells_stride]  histogram, then scatter cursor
   int* cell_of;         // [N, m]
   void* recs;           // [N, m] GridRec<T>
-  int* max_occupancy;   // [1]
+  int* max_occupancy;   // [2]
+  int* q_cell_start;    // [N, cells_stride]  query sort
+  int* q_cell_of;       // [N, n]
+  int* q_order;         // [N, n]  query indices in cell order
   int cells_stride;
   size_t total;
 };
-GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int m, int elem_size);
+GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size);
 template <typename T> int grid_build(const T* tgt, int N, int m, int S, const GridWorkspace& g, cudaStream_t st);
+template <typename T> int grid_sort_queries(const T* q, const double* state, int N, int n, const GridWorkspace& g, cudaStream_t st);
 template <typename T>
-int grid_search(const T* q, const double* state, int N, int n, int m, const GridWorkspace& g, int32_t* idx_out, T* d2_out,
+int grid_search(const T* q, const double* state, int N, int n, int m, const GridWorkspace& g, bool sorted, int32_t* idx_out, T* d2_out,
                 const int* stop_flag, cudaStream_t st);
 
 // ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------

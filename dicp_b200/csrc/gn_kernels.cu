@@ -274,7 +274,7 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
   w.ctrl = ar.take<Ctrl>(1);
   w.bw_state = ar.take<double>((size_t)N * BW_STRIDE);
   w.bw_partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * BW_NRED);
-  w.grid_ws_bytes = grid_ws_layout(nullptr, 0, N, m, elem_size).total;
+  w.grid_ws_bytes = grid_ws_layout(nullptr, 0, N, n, m, elem_size).total;
   w.grid_ws = ar.take<char>(w.grid_ws_bytes);
   w.total = ar.off;
   return w;
@@ -321,8 +321,10 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   bool use_grid = p->nn_mode == DICP_NN_GRID;
   GridWorkspace gw;
   if (use_grid) {
-    gw = grid_ws_layout(w.grid_ws, w.grid_ws_bytes, N, m, sizeof(T));
+    gw = grid_ws_layout(w.grid_ws, w.grid_ws_bytes, N, n, m, sizeof(T));
     rc = grid_build<T>(target, N, m, S, gw, st);
+    if (rc) return rc;
+    rc = grid_sort_queries<T>(source, saved_state, N, n, gw, st);      // at the initial transform (record 0)
     if (rc) return rc;
     int max_occ = 0;
     DICP_CUDA(cudaMemcpyAsync(&max_occ, gw.max_occupancy, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -335,7 +337,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   for (int k = 0; k < K; ++k) {
     double* rec_k = saved_state + (size_t)k * rec_stride;
     int32_t* idx_k = saved_idx + (size_t)k * N * n;
-    if (use_grid) rc = grid_search<T>(source, rec_k, N, n, m, gw, idx_k, nullptr, &w.ctrl->stop, st);
+    if (use_grid) rc = grid_search<T>(source, rec_k, N, n, m, gw, true, idx_k, nullptr, &w.ctrl->stop, st);
     else rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st);
     if (rc) return rc;
     rc = gn_accumulate<T>(source, target, w_init, idx_k, rec_k, N, n, m, S, p,

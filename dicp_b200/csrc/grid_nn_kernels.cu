@@ -8,14 +8,18 @@
 //   grid_count_kernel    histogram of targets per cell (atomicAdd)
 //   grid_scan_kernel     exclusive prefix sum per pair (one CTA per pair) -> cell_start
 //   grid_scatter_kernel  counting-sort scatter of (x,y,z,index) records into cell order
-//   grid_query_kernel    one thread per query: visit the cells ring by ring (Chebyshev distance
-//                        0,1,2,.. around the query's cell), direct-form fp32/fp64 distance to every
+//   grid_q*_kernel       counting sort of the queries by the cell of their initial position (once per
+//                        call), so that the lanes of a warp search neighbouring cells
+//   grid_query_kernel    one thread per query: visit the 3x3x3 block around the query's cell, then
+//                        ring by ring (Chebyshev distance 2,3,..), direct-form fp32/fp64 distance to every
 //                        record, lexicographic (d2, index) minimum; stop as soon as the best
 //                        distance is strictly smaller than the distance from the query to the
 //                        faces of the visited block behind which unvisited cells remain.
 // The result is the same argmin the brute-force search returns (same direct-form arithmetic,
 // same first-minimum tie-break); tests compare the two bit for bit.  Memory- and latency-bound
 // (scattered 16-byte record reads from L2), O(n) per pair instead of O(n*m).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dicp {
@@ -31,7 +35,7 @@ template <typename T> struct GridRec { T x, y, z; int idx; };
 struct GridDims { int nx, ny, nz; };
 
 template <typename T>
-__global__ void grid_bbox_kernel(const T* __restrict__ tgt, int m, int S, int cells_cap, double* __restrict__ gparams,
+__global__ void grid_bbox_kernel(const T* __restrict__ tgt, int m, int S, int cells_cap, double hscale, double* __restrict__ gparams,
                                  int* __restrict__ gdims) {
   __shared__ double smin[3][8], smax[3][8];
   const int b = blockIdx.x;
@@ -66,7 +70,7 @@ __global__ void grid_bbox_kernel(const T* __restrict__ tgt, int m, int S, int ce
     const double floor_ext = fmax(emax * 1e-3, 1e-30);               // flat / degenerate clouds: thin slab, not zero volume
     double vol = 1.0;
     for (int c = 0; c < 3; ++c) vol *= fmax(ext[c], floor_ext);
-    double h = cbrt(vol / (double)m);
+    double h = hscale * cbrt(vol / (double)m);
     if (!(h > 0.0)) h = 1.0;
     int d[3];
     for (int it = 0; it < 64; ++it) {
@@ -173,16 +177,31 @@ __global__ void grid_scatter_kernel(const T* __restrict__ tgt, int m, int S, int
   recs[(size_t)b * m + pos] = r;
 }
 
+// visit the records of cells [c0, c1] of one grid row (contiguous in the sorted record array)
+template <typename T>
+__device__ __forceinline__ void grid_visit_run(const int* __restrict__ cs, const GridRec<T>* __restrict__ rb, int c0, int c1,
+                                               T x0, T x1, T x2, T& best, int& bi) {
+  const int s = cs[c0], e = cs[c1 + 1];
+  for (int k = s; k < e; ++k) {
+    const GridRec<T> t = rb[k];
+    const T d = dist2<T>(x0, x1, x2, t.x, t.y, t.z);
+    if (d < best || (d == best && t.idx < bi)) { best = d; bi = t.idx; }      // lexicographic: first minimum
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 grid_query_kernel(const T* __restrict__ q, const double* __restrict__ state, int n, int m, int cells_stride,
                   const double* __restrict__ gparams, const int* __restrict__ gdims, const int* __restrict__ cell_start,
-                  const GridRec<T>* __restrict__ recs, int32_t* __restrict__ idx_out, T* __restrict__ d2_out,
-                  const int* __restrict__ stop_flag) {
+                  const GridRec<T>* __restrict__ recs, const int* __restrict__ order, int32_t* __restrict__ idx_out,
+                  T* __restrict__ d2_out, const int* __restrict__ stop_flag) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n) return;
+  // queries are processed in the cell order of their initial position, so the lanes of a warp walk
+  // the same few cells (coalesced / broadcast record reads, similar trip counts)
+  const int i = order != nullptr ? order[(size_t)b * n + slot] : slot;
   const T* p = q + ((size_t)b * n + i) * 3;
   T x0 = p[0], x1 = p[1], x2 = p[2];
   if (state != nullptr) {
@@ -206,41 +225,20 @@ grid_query_kernel(const T* __restrict__ q, const double* __restrict__ state, int
   T best = sizeof(T) == 4 ? (T)__int_as_float(0x7f800000) : (T)__longlong_as_double(0x7ff0000000000000LL);
   int bi = 0x7fffffff;
   const int rmax = max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz));
-  for (int r = 0; r <= rmax; ++r) {
+  constexpr int R0 = 1;                       // the 3x3x3 block around the query's cell is visited first, as 9 row runs
+  for (int r = R0; r <= max(rmax, R0); ++r) {
     const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
     const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
     const int xa = max(cx - r, 0), xb = min(cx + r, nx - 1);
     for (int z = z0; z <= z1; ++z) {
-      const bool zface = (z == cz - r) || (z == cz + r);
+      const bool zface = (r == R0) || (z == cz - r) || (z == cz + r);
       for (int y = y0; y <= y1; ++y) {
-        const bool yface = zface || (y == cy - r) || (y == cy + r);
         const int rowbase = (z * ny + y) * nx;
-        if (yface) {
-          // the whole x-run of this row belongs to ring r: its cells are contiguous in memory
-          const int s = cs[rowbase + xa], e = cs[rowbase + xb + 1];
-          for (int k = s; k < e; ++k) {
-            const GridRec<T> t = rb[k];
-            const T d = dist2<T>(x0, x1, x2, t.x, t.y, t.z);
-            if (d < best || (d == best && t.idx < bi)) { best = d; bi = t.idx; }
-          }
-        } else {
-          // interior row: only the two end cells (x = cx-r and x = cx+r) are on the ring
-          if (cx - r >= 0) {
-            const int s = cs[rowbase + cx - r], e = cs[rowbase + cx - r + 1];
-            for (int k = s; k < e; ++k) {
-              const GridRec<T> t = rb[k];
-              const T d = dist2<T>(x0, x1, x2, t.x, t.y, t.z);
-              if (d < best || (d == best && t.idx < bi)) { best = d; bi = t.idx; }
-            }
-          }
-          if (r > 0 && cx + r <= nx - 1) {
-            const int s = cs[rowbase + cx + r], e = cs[rowbase + cx + r + 1];
-            for (int k = s; k < e; ++k) {
-              const GridRec<T> t = rb[k];
-              const T d = dist2<T>(x0, x1, x2, t.x, t.y, t.z);
-              if (d < best || (d == best && t.idx < bi)) { best = d; bi = t.idx; }
-            }
-          }
+        if (zface || (y == cy - r) || (y == cy + r)) {
+          grid_visit_run<T>(cs, rb, rowbase + xa, rowbase + xb, x0, x1, x2, best, bi);      // whole x-run is on the ring / in the block
+        } else {                                                                              // interior row: the two end cells
+          if (cx - r >= 0) grid_visit_run<T>(cs, rb, rowbase + cx - r, rowbase + cx - r, x0, x1, x2, best, bi);
+          if (cx + r <= nx - 1) grid_visit_run<T>(cs, rb, rowbase + cx + r, rowbase + cx + r, x0, x1, x2, best, bi);
         }
       }
     }
@@ -260,15 +258,54 @@ grid_query_kernel(const T* __restrict__ q, const double* __restrict__ state, int
   if (d2_out != nullptr) d2_out[o] = best;
 }
 
+// counting sort of the queries by the grid cell of their (transformed) position -> order[b, 0..n)
+template <typename T>
+__global__ void grid_qcount_kernel(const T* __restrict__ q, const double* __restrict__ state, int n, int cells_stride,
+                                   const double* __restrict__ gparams, const int* __restrict__ gdims, int* __restrict__ cell_count,
+                                   int* __restrict__ cell_of) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T* p = q + ((size_t)b * n + i) * 3;
+  T x0 = p[0], x1 = p[1], x2 = p[2];
+  if (state != nullptr) {
+    const double* rec = state + (size_t)b * ST_STRIDE;
+    T C[9], pv[3] = {x0, x1, x2}, a[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) C[k] = (T)rec[ST_C + k];
+    rotate(C, pv, a);
+    x0 = a[0] + (T)rec[ST_R]; x1 = a[1] + (T)rec[ST_R + 1]; x2 = a[2] + (T)rec[ST_R + 2];
+  }
+  const double* gp = gparams + (size_t)b * GP_STRIDE;
+  const int* gd = gdims + (size_t)b * 4;
+  const int cx = cell_coord((double)x0, gp[GP_ORIGIN], gp[GP_INVH], gd[0]);
+  const int cy = cell_coord((double)x1, gp[GP_ORIGIN + 1], gp[GP_INVH], gd[1]);
+  const int cz = cell_coord((double)x2, gp[GP_ORIGIN + 2], gp[GP_INVH], gd[2]);
+  const int cell = (cz * gd[1] + cy) * gd[0] + cx;
+  cell_of[(size_t)b * n + i] = cell;
+  atomicAdd(&cell_count[(size_t)b * cells_stride + cell], 1);
+}
+__global__ void grid_qscatter_kernel(int n, int cells_stride, const int* __restrict__ cell_of, const int* __restrict__ cell_start,
+                                     int* __restrict__ cell_cursor, int* __restrict__ order) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cell = cell_of[(size_t)b * n + i];
+  const int pos = cell_start[(size_t)b * cells_stride + cell] + atomicAdd(&cell_cursor[(size_t)b * cells_stride + cell], 1);
+  order[(size_t)b * n + pos] = i;
+}
+
+constexpr double GRID_HSCALE = 0.6;   // cell size in units of cbrt(box volume / m)
+
 // ---- host side --------------------------------------------------------------------------------
 int grid_cells_cap(int m) {
-  long long c = 4LL * m;
+  long long c = 8LL * m;
   if (c < 64) c = 64;
   if (c > (1LL << 22)) c = 1LL << 22;
   return (int)c;
 }
 
-GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int m, int elem_size) {
+GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size) {
   Arena ar(ws, ws_bytes);
   GridWorkspace g;
   g.cells_stride = grid_cells_cap(m) + 1;
@@ -278,7 +315,10 @@ GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int m, int elem_s
   g.cell_count = ar.take<int>((size_t)N * g.cells_stride);      // reused as the scatter cursor
   g.cell_of = ar.take<int>((size_t)N * m);
   g.recs = ar.take<char>((size_t)N * m * (elem_size == 4 ? sizeof(GridRec<float>) : sizeof(GridRec<double>)));
-  g.max_occupancy = ar.take<int>(1);
+  g.max_occupancy = ar.take<int>(2);                            // [0] targets, [1] scratch for the query sort
+  g.q_cell_start = ar.take<int>((size_t)N * g.cells_stride);
+  g.q_cell_of = ar.take<int>((size_t)N * n);
+  g.q_order = ar.take<int>((size_t)N * n);
   g.total = ar.off;
   return g;
 }
@@ -288,7 +328,9 @@ int grid_build(const T* tgt, int N, int m, int S, const GridWorkspace& g, cudaSt
   const int cap = grid_cells_cap(m);
   DICP_CUDA(cudaMemsetAsync(g.cell_count, 0, sizeof(int) * (size_t)N * g.cells_stride, st));
   DICP_CUDA(cudaMemsetAsync(g.max_occupancy, 0, sizeof(int), st));
-  grid_bbox_kernel<T><<<N, 256, 0, st>>>(tgt, m, S, cap, g.gparams, g.gdims);
+  const char* hs = getenv("DICP_GRID_HSCALE");            // tuning knob (tools/prof_grid.py); default GRID_HSCALE
+  const double hscale = hs != nullptr ? atof(hs) : GRID_HSCALE;
+  grid_bbox_kernel<T><<<N, 256, 0, st>>>(tgt, m, S, cap, hscale, g.gparams, g.gdims);
   DICP_LAUNCH_CHECK();
   dim3 grid((m + 255) / 256, N);
   grid_count_kernel<T><<<grid, 256, 0, st>>>(tgt, m, S, g.cells_stride, g.gparams, g.gdims, g.cell_count, g.cell_of);
@@ -303,35 +345,54 @@ int grid_build(const T* tgt, int N, int m, int S, const GridWorkspace& g, cudaSt
 template int grid_build<float>(const float*, int, int, int, const GridWorkspace&, cudaStream_t);
 template int grid_build<double>(const double*, int, int, int, const GridWorkspace&, cudaStream_t);
 
+// sort the queries by cell (once per call, at their initial position): g.q_order
 template <typename T>
-int grid_search(const T* q, const double* state, int N, int n, int m, const GridWorkspace& g, int32_t* idx_out, T* d2_out,
-                const int* stop_flag, cudaStream_t st) {
-  dim3 grid((n + 127) / 128, N);
-  grid_query_kernel<T><<<grid, 128, 0, st>>>(q, state, n, m, g.cells_stride, g.gparams, g.gdims, g.cell_start, (const GridRec<T>*)g.recs,
-                                             idx_out, d2_out, stop_flag);
+int grid_sort_queries(const T* q, const double* state, int N, int n, const GridWorkspace& g, cudaStream_t st) {
+  DICP_CUDA(cudaMemsetAsync(g.cell_count, 0, sizeof(int) * (size_t)N * g.cells_stride, st));
+  dim3 grid((n + 255) / 256, N);
+  grid_qcount_kernel<T><<<grid, 256, 0, st>>>(q, state, n, g.cells_stride, g.gparams, g.gdims, g.cell_count, g.q_cell_of);
+  DICP_LAUNCH_CHECK();
+  grid_scan_kernel<<<N, 1024, 0, st>>>(g.cell_count, g.cells_stride, g.gdims, g.q_cell_start, g.max_occupancy + 1);
+  DICP_LAUNCH_CHECK();
+  DICP_CUDA(cudaMemsetAsync(g.cell_count, 0, sizeof(int) * (size_t)N * g.cells_stride, st));
+  grid_qscatter_kernel<<<grid, 256, 0, st>>>(n, g.cells_stride, g.q_cell_of, g.q_cell_start, g.cell_count, g.q_order);
   DICP_LAUNCH_CHECK();
   return 0;
 }
-template int grid_search<float>(const float*, const double*, int, int, int, const GridWorkspace&, int32_t*, float*, const int*, cudaStream_t);
-template int grid_search<double>(const double*, const double*, int, int, int, const GridWorkspace&, int32_t*, double*, const int*, cudaStream_t);
+template int grid_sort_queries<float>(const float*, const double*, int, int, const GridWorkspace&, cudaStream_t);
+template int grid_sort_queries<double>(const double*, const double*, int, int, const GridWorkspace&, cudaStream_t);
+
+template <typename T>
+int grid_search(const T* q, const double* state, int N, int n, int m, const GridWorkspace& g, bool sorted, int32_t* idx_out, T* d2_out,
+                const int* stop_flag, cudaStream_t st) {
+  dim3 grid((n + 127) / 128, N);
+  grid_query_kernel<T><<<grid, 128, 0, st>>>(q, state, n, m, g.cells_stride, g.gparams, g.gdims, g.cell_start, (const GridRec<T>*)g.recs,
+                                             sorted ? g.q_order : nullptr, idx_out, d2_out, stop_flag);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+template int grid_search<float>(const float*, const double*, int, int, int, const GridWorkspace&, bool, int32_t*, float*, const int*, cudaStream_t);
+template int grid_search<double>(const double*, const double*, int, int, int, const GridWorkspace&, bool, int32_t*, double*, const int*, cudaStream_t);
 
 template <typename T>
 static int nn_argmin_grid_impl(const T* q, const T* tgt, int N, int n, int m, int S, int32_t* idx_out, T* d2_out, void* ws,
                                size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(q && tgt && idx_out, "null pointer");
   DICP_CHECK_ARG(N >= 1 && N <= 65535 && n >= 1 && m >= 1 && (S == 3 || S == 6), "bad sizes");
-  const GridWorkspace g = grid_ws_layout(ws, ws_bytes, N, m, sizeof(T));
+  const GridWorkspace g = grid_ws_layout(ws, ws_bytes, N, n, m, sizeof(T));
   if (ws == nullptr || g.total > ws_bytes) { set_error("dicp_nn_argmin_grid: workspace too small"); return DICP_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   int rc = grid_build<T>(tgt, N, m, S, g, st);
   if (rc) return rc;
-  return grid_search<T>(q, nullptr, N, n, m, g, idx_out, d2_out, nullptr, st);
+  rc = grid_sort_queries<T>(q, nullptr, N, n, g, st);
+  if (rc) return rc;
+  return grid_search<T>(q, nullptr, N, n, m, g, true, idx_out, d2_out, nullptr, st);
 }
 
 }  // namespace dicp
 
 extern "C" {
-size_t dicp_nn_grid_workspace_bytes(int N, int m, int elem_size) { return dicp::grid_ws_layout(nullptr, 0, N, m, elem_size).total; }
+size_t dicp_nn_grid_workspace_bytes(int N, int n, int m, int elem_size) { return dicp::grid_ws_layout(nullptr, 0, N, n, m, elem_size).total; }
 int dicp_nn_argmin_grid_f32(const float* q, const float* tgt, int N, int n, int m, int S, int32_t* idx_out, float* d2_out, void* ws,
                             size_t ws_bytes, void* stream) {
   return dicp::nn_argmin_grid_impl<float>(q, tgt, N, n, m, S, idx_out, d2_out, ws, ws_bytes, stream);

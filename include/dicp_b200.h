@@ -95,7 +95,7 @@ DICP_API int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n
 
 /* Same result through a uniform grid: build (bounding box, counting sort)
  * + one-thread-per-query ring search.  ws sized by dicp_nn_grid_workspace_bytes.             */
-DICP_API size_t dicp_nn_grid_workspace_bytes(int N, int m, int elem_size);
+DICP_API size_t dicp_nn_grid_workspace_bytes(int N, int n, int m, int elem_size);
 DICP_API int dicp_nn_argmin_grid_f32(const float* q, const float* tgt, int N, int n, int m, int S,
                             int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
 DICP_API int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, int n, int m, int S,

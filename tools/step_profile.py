@@ -12,6 +12,7 @@ import bench  # noqa: E402
 from dICP.ICP import ICP  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+MODE = sys.argv[2] if len(sys.argv) > 2 else "brute"
 dev = torch.device("cuda")
 src, tgt = bench.make_batch(N, 0)
 src = src.to(dev).requires_grad_(True)
@@ -19,6 +20,7 @@ tgt = tgt.to(dev).requires_grad_(True)
 T0 = torch.eye(4, device=dev).repeat(N, 1, 1)
 icp = ICP(icp_type="pt2pl", differentiable=True, max_iterations=10, tolerance=1e-12)
 icp.const_iter = True
+icp.nn_search = MODE
 theta = torch.arange(1, 13, dtype=torch.float32, device=dev)
 
 
