@@ -154,10 +154,7 @@ bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, co
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const T* row = tgt_b + (size_t)jj[u] * S;
-        q[u][0] = row[0]; q[u][1] = row[1]; q[u][2] = row[2];
-        if (PT2PL) { nr[u][0] = row[3]; nr[u][1] = row[4]; nr[u][2] = row[5]; }
-        else { nr[u][0] = nr[u][1] = nr[u][2] = T(0); }
+        load_target_row<T, PT2PL>(tgt_b + (size_t)jj[u] * S, S, q[u], nr[u]);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -171,11 +168,12 @@ bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, co
 #pragma unroll
         for (int c = 0; c < 3; ++c) gs_b[3 * i + c] += C[c] * abar[0] + C[3 + c] * abar[1] + C[6 + c] * abar[2];   // C^T abar
         T* grow = gt_b + (size_t)jj[u] * S;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(grow + c, -ebar[c]);
         if (PT2PL) {
+          const T g6[6] = {-ebar[0], -ebar[1], -ebar[2], nbar[0], nbar[1], nbar[2]};
+          atomic_add_row6(grow, g6);
+        } else {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) atomicAdd(grow + 3 + c, nbar[c]);
+          for (int c = 0; c < 3; ++c) atomicAdd(grow + c, -ebar[c]);
         }
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) {

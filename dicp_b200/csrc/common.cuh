@@ -66,6 +66,32 @@ inline WeightParams make_weight_params(const dicp_params* p) {
   return w;
 }
 
+#if defined(__CUDACC__)
+// gather of one target row (S = 3 | 6 columns, 8-byte aligned when S == 6 or the row index is even)
+template <typename T, bool PT2PL>
+__device__ __forceinline__ void load_target_row(const T* __restrict__ row, int S, T* q, T* nr) {
+  if (PT2PL && sizeof(T) == 4) {            // 24-byte rows: three 8-byte loads
+    const float2 a = *reinterpret_cast<const float2*>(row), b = *reinterpret_cast<const float2*>(row + 2),
+                 c = *reinterpret_cast<const float2*>(row + 4);
+    q[0] = (T)a.x; q[1] = (T)a.y; q[2] = (T)b.x; nr[0] = (T)b.y; nr[1] = (T)c.x; nr[2] = (T)c.y;
+  } else {
+    q[0] = row[0]; q[1] = row[1]; q[2] = row[2];
+    if (PT2PL) { nr[0] = row[3]; nr[1] = row[4]; nr[2] = row[5]; }
+    else { nr[0] = nr[1] = nr[2] = T(0); }
+  }
+}
+// scatter-add of one 6-column gradient row: fp32 uses the 8-byte vector reduction (red.global.add.v2.f32)
+__device__ __forceinline__ void atomic_add_row6(float* row, const float* v) {
+  atomicAdd(reinterpret_cast<float2*>(row), make_float2(v[0], v[1]));
+  atomicAdd(reinterpret_cast<float2*>(row + 2), make_float2(v[2], v[3]));
+  atomicAdd(reinterpret_cast<float2*>(row + 4), make_float2(v[4], v[5]));
+}
+__device__ __forceinline__ void atomic_add_row6(double* row, const double* v) {
+#pragma unroll
+  for (int c = 0; c < 6; ++c) atomicAdd(row + c, v[c]);
+}
+#endif
+
 // device control block of one forward call
 struct Ctrl {
   int stop;        // all pairs below tolerance (only raised when !const_iter)

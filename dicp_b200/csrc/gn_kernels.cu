@@ -106,17 +106,14 @@ gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, cons
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const T* row = tgt_b + (size_t)jj[u] * S;
-      q[u][0] = row[0]; q[u][1] = row[1]; q[u][2] = row[2];
-      if (PT2PL) { nr[u][0] = row[3]; nr[u][1] = row[4]; nr[u][2] = row[5]; }
-      else { nr[u][0] = nr[u][1] = nr[u][2] = T(0); }
+      load_target_row<T, PT2PL>(tgt_b + (size_t)jj[u] * S, S, q[u], nr[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (ii[u] < 0) continue;
       PointEval<T> s;
       eval_point<T, PT2PL>(C, r, p[u], q[u], nr[u], w0[u], P, s);
-      accum_point<T, PT2PL, DIM>(acc, s, w0[u], P.thresh);
+      accum_point<T, PT2PL, DIM>(acc, s, w0[u], (T)P.thresh);
       if (wout != nullptr) {
 #pragma unroll
         for (int k = 0; k < R; ++k) wout[(size_t)ii[u] * R + k] = s.w;                      // ICP.py:222, 164-165

@@ -41,7 +41,7 @@ static void accum_pair(const T* src, const T* tgt, const T* w_init, const int32_
       const T w0 = (w_init ? w_init[i] : T(1)) * active;
       PointEval<T> s;
       eval_point<T, PL>(C, r, p, row, nr, w0, P, s);
-      accum_point<T, PL, DIM>(acc, s, w0, P.thresh);
+      accum_point<T, PL, DIM>(acc, s, w0, (T)P.thresh);
       const int R = PL ? 1 : 3;
       if (wout) for (int k = 0; k < R; ++k) wout[(size_t)i * R + k] = s.w;
     }
