@@ -62,6 +62,11 @@ class ICP:
         'costs' (N,K,1), 'deltas' (N,K,6,1), 'weights' (N,K,n|3n,1) and 'stats'
         {'converged','iterations','matched_ratio'} (each (N,))."""
         assert dim == 2 or dim == 3, "dim must be 2 or 3"
+        # ragged target lists: remember the real length of every cloud so that the padding rows
+        # (ICP.py:471-479) can never be returned as a neighbour, whatever max(source) * target_pad_val is
+        m_valid = None
+        if isinstance(target, list) and len(target) > 0 and not _is_empty(source):
+            m_valid = [max(len(t_i), 1) for t_i in target]
         source, target, T_init, w_init = self.batch_size_handling(source, target, T_init, weight)
         assert source.dtype == target.dtype == T_init.dtype
         N, n = source.shape[0], source.shape[1]
@@ -96,8 +101,12 @@ class ICP:
             self.config['dICP']['parameters']['tanh_steepness'], self.tolerance, self.max_iterations,
             self.const_iter, self.match_ratio_thresh, self.check_every, self.nn_search)
 
+        if m_valid is not None and (len(m_valid) != N or min(m_valid) == target.shape[1]):
+            m_valid = None                                   # nothing is padded
+        if m_valid is not None:
+            m_valid = torch.tensor(m_valid, dtype=torch.int32, device=dev)
         pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
-            source.to(dev), target.to(dev), T_init.to(dev), w_point.to(dev), params)
+            source.to(dev), target.to(dev), T_init.to(dev), w_point.to(dev), params, m_valid)
 
         if self.verbose:
             print("ICP converged in {} iterations".format(deltas.shape[1]))

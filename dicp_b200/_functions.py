@@ -137,10 +137,11 @@ class ICPFunction(torch.autograd.Function):
 
     forward(source (N,n,3), target (N,m,S), T_init (N,4,4), w_init (N,n) | None, params)
       -> pc, T (differentiable) and deltas, weights, costs, converged, num_iters, match_ratio
-         (detached / non-differentiable, ICP.py:220-229, 288-292)."""
+         (detached / non-differentiable, ICP.py:220-229, 288-292).
+    m_valid (N,) int32 or None: real row count of every target cloud of a ragged batch."""
 
     @staticmethod
-    def forward(ctx, source, target, T_init, w_init, params):
+    def forward(ctx, source, target, T_init, w_init, params, m_valid=None):
         require_cuda()
         lib = load_library()
         dev, dt = source.device, source.dtype
@@ -167,7 +168,7 @@ class ICPFunction(torch.autograd.Function):
         iters = ctypes.c_int32(0)
         with torch.cuda.device(dev):
             rc = getattr(lib, "dicp_icp_forward_" + sfx)(
-                ptr(source), ptr(target), ptr(T_init), ptr(w_init), N, n, m, S, ctypes.byref(params),
+                ptr(source), ptr(target), ptr(T_init), ptr(w_init), ptr(m_valid), N, n, m, S, ctypes.byref(params),
                 ptr(pc), ptr(T), ptr(deltas), ptr(weights), ptr(costs), ptr(converged), ptr(num_iters), ptr(match_ratio),
                 ptr(saved_idx), ptr(saved_state), ctypes.byref(iters), ptr(ws), ws.numel(), stream_ptr(dev))
         check(rc, "dicp_icp_forward_" + sfx)
@@ -203,4 +204,4 @@ class ICPFunction(torch.autograd.Function):
                 ptr(saved_idx), ptr(saved_state), ptr(g_T), ptr(g_pc), ptr(g_src), ptr(g_tgt), ptr(g_w), ptr(g_T0),
                 ptr(ws), ws.numel(), stream_ptr(dev))
         check(rc, "dicp_icp_backward_" + sfx)
-        return g_src, g_tgt, g_T0, g_w, None
+        return g_src, g_tgt, g_T0, g_w, None, None

@@ -202,7 +202,7 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
   cudaStream_t st = (cudaStream_t)stream;
   IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T));
   const WeightParams P = make_weight_params(p);
-  const int nblk = gn_blocks_per_pair(n);
+  const int nblk = bw_blocks_per_pair(n);
   const size_t rec_stride = (size_t)N * ST_STRIDE;
   const bool pl = p->icp_type == DICP_PT2PL;
   dim3 pgrid(nblk, N);

@@ -114,7 +114,7 @@ inline int nn_m_pad(int m) { return (m + NN_CHUNK - 1) / NN_CHUNK * NN_CHUNK; }
 inline size_t nn_packed_bytes(int N, int m, int elem_size) { return align_up((size_t)N * nn_m_pad(m) * 4 * elem_size); }
 
 template <typename T>
-int nn_pack_targets(const T* tgt, int N, int m, int S, typename Vec4<T>::type* packed, cudaStream_t st);
+int nn_pack_targets(const T* tgt, int N, int m, int S, const int32_t* m_valid, typename Vec4<T>::type* packed, cudaStream_t st);
 // state: nullptr (queries are used as given) or pointer to this iteration's saved-state
 // records [N, ST_STRIDE] whose C,r transform the queries first (ICP.py:137).
 template <typename T>
@@ -138,7 +138,7 @@ struct GridWorkspace {
   size_t total;
 };
 GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size);
-template <typename T> int grid_build(const T* tgt, int N, int m, int S, const GridWorkspace& g, cudaStream_t st);
+template <typename T> int grid_build(const T* tgt, int N, int m, int S, const int32_t* m_valid, const GridWorkspace& g, cudaStream_t st);
 template <typename T> int grid_sort_queries(const T* q, const double* state, int N, int n, const GridWorkspace& g, cudaStream_t st);
 template <typename T>
 int grid_search(const T* q, const double* state, int N, int n, int m, const GridWorkspace& g, bool sorted, int32_t* idx_out, T* d2_out,
@@ -146,6 +146,7 @@ int grid_search(const T* q, const double* state, int N, int n, int m, const Grid
 
 // ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------
 int gn_blocks_per_pair(int n);
+int bw_blocks_per_pair(int n);
 template <typename T>
 int gn_accumulate(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* state,
                   int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,

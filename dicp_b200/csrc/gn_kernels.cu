@@ -28,7 +28,14 @@ void set_error(const char* fmt, ...) {
 }
 
 constexpr int GN_THREADS = 128;
-constexpr int GN_PTS_PER_THREAD = 8;   // 2 passes of 4: amortises the 31-value block reduction
+constexpr int GN_PTS_PER_THREAD = 16;  // 4 passes of 4: amortises the 31-value block reduction
+
+int bw_blocks_per_pair(int n) {          // backward point pass: 8 correspondences per thread (2 passes of 4)
+  int nb = (n + GN_THREADS * 8 - 1) / (GN_THREADS * 8);
+  if (nb < 1) nb = 1;
+  if (nb > 128) nb = 128;
+  return nb;
+}
 
 int gn_blocks_per_pair(int n) {
   int nb = (n + GN_THREADS * GN_PTS_PER_THREAD - 1) / (GN_THREADS * GN_PTS_PER_THREAD);
@@ -270,7 +277,7 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
   w.partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * RED_N);
   w.ctrl = ar.take<Ctrl>(1);
   w.bw_state = ar.take<double>((size_t)N * BW_STRIDE);
-  w.bw_partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * BW_NRED);
+  w.bw_partials = ar.take<double>((size_t)N * bw_blocks_per_pair(n) * BW_NRED);
   w.grid_ws_bytes = grid_ws_layout(nullptr, 0, N, n, m, elem_size).total;
   w.grid_ws = ar.take<char>(w.grid_ws_bytes);
   w.total = ar.off;
@@ -278,8 +285,8 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
 }
 
 template <typename T>
-static int icp_forward_impl(const T* source, const T* target, const T* T_init, const T* w_init, int N, int n, int m, int S,
-                            const dicp_params* p, T* pc, T* T_out, T* deltas, T* weights, T* costs, uint8_t* converged,
+static int icp_forward_impl(const T* source, const T* target, const T* T_init, const T* w_init, const int32_t* m_valid, int N, int n,
+                            int m, int S, const dicp_params* p, T* pc, T* T_out, T* deltas, T* weights, T* costs, uint8_t* converged,
                             T* num_iters, T* match_ratio, int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
                             void* ws, size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(source && target && T_init && p && pc && T_out && deltas && costs && converged && num_iters && match_ratio &&
@@ -309,9 +316,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   DICP_CUDA(cudaMemsetAsync(w.ctrl, 0, sizeof(Ctrl), st));
   init_state_kernel<T><<<(N + 127) / 128, 128, 0, st>>>(T_init, N, saved_state, converged, num_iters, match_ratio);
   DICP_LAUNCH_CHECK();
-  int rc = nn_pack_targets<T>(target, N, m, S, (V4*)w.packed, st);
-  if (rc) return rc;
-
+  int rc = 0;
   // optional spatial index of the (static) targets; a cloud so clustered that one cell holds a
   // large share of it (e.g. the 1000 x max(source) padding rows of a ragged batch stretch the
   // bounding box) would make the ring search degenerate, so such calls keep the tiled scan
@@ -319,7 +324,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   GridWorkspace gw;
   if (use_grid) {
     gw = grid_ws_layout(w.grid_ws, w.grid_ws_bytes, N, n, m, sizeof(T));
-    rc = grid_build<T>(target, N, m, S, gw, st);
+    rc = grid_build<T>(target, N, m, S, m_valid, gw, st);
     if (rc) return rc;
     rc = grid_sort_queries<T>(source, saved_state, N, n, gw, st);      // at the initial transform (record 0)
     if (rc) return rc;
@@ -327,6 +332,10 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
     DICP_CUDA(cudaMemcpyAsync(&max_occ, gw.max_occupancy, sizeof(int), cudaMemcpyDeviceToHost, st));
     DICP_CUDA(cudaStreamSynchronize(st));
     if (max_occ > 64 && max_occ > m / 64) use_grid = false;
+  }
+  if (!use_grid) {
+    rc = nn_pack_targets<T>(target, N, m, S, m_valid, (V4*)w.packed, st);
+    if (rc) return rc;
   }
 
   Ctrl h;
@@ -416,18 +425,18 @@ size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size) {
   return dicp::plan_workspace(nullptr, 0, N, n, m, elem_size).total;
 }
 
-int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init, int N, int n, int m,
-                         int S, const dicp_params* params, float* pc, float* T_out, float* deltas, float* weights, float* costs,
+int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init, const int32_t* m_valid,
+                         int N, int n, int m, int S, const dicp_params* params, float* pc, float* T_out, float* deltas, float* weights, float* costs,
                          uint8_t* converged, float* num_iters, float* match_ratio, int32_t* saved_idx, double* saved_state,
                          int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream) {
-  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                        converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
 }
-int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init, int N, int n,
-                         int m, int S, const dicp_params* params, double* pc, double* T_out, double* deltas, double* weights,
+int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init, const int32_t* m_valid,
+                         int N, int n, int m, int S, const dicp_params* params, double* pc, double* T_out, double* deltas, double* weights,
                          double* costs, uint8_t* converged, double* num_iters, double* match_ratio, int32_t* saved_idx,
                          double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream) {
-  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                         converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
 }
 int dicp_gn_accumulate_f32(const float* source, const float* target, const float* w_init, const int32_t* idx, const double* C_r,

@@ -35,11 +35,12 @@ template <typename T> struct GridRec { T x, y, z; int idx; };
 struct GridDims { int nx, ny, nz; };
 
 template <typename T>
-__global__ void grid_bbox_kernel(const T* __restrict__ tgt, int m, int S, int cells_cap, double hscale, double* __restrict__ gparams,
-                                 int* __restrict__ gdims) {
+__global__ void grid_bbox_kernel(const T* __restrict__ tgt, int m_all, int S, const int32_t* __restrict__ m_valid, int cells_cap,
+                                 double hscale, double* __restrict__ gparams, int* __restrict__ gdims) {
   __shared__ double smin[3][8], smax[3][8];
   const int b = blockIdx.x;
-  const T* tb = tgt + (size_t)b * m * S;
+  const T* tb = tgt + (size_t)b * m_all * S;
+  const int m = m_valid != nullptr ? min(max(m_valid[b], 1), m_all) : m_all;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
 #pragma unroll
@@ -99,11 +100,12 @@ __device__ __forceinline__ int cell_coord(double v, double origin, double invh, 
 }
 
 template <typename T>
-__global__ void grid_count_kernel(const T* __restrict__ tgt, int m, int S, int cells_stride, const double* __restrict__ gparams,
-                                  const int* __restrict__ gdims, int* __restrict__ cell_count, int* __restrict__ cell_of) {
+__global__ void grid_count_kernel(const T* __restrict__ tgt, int m, int S, const int32_t* __restrict__ m_valid, int cells_stride,
+                                  const double* __restrict__ gparams, const int* __restrict__ gdims, int* __restrict__ cell_count,
+                                  int* __restrict__ cell_of) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
+  if (j >= (m_valid != nullptr ? min(max(m_valid[b], 1), m) : m)) return;
   const double* gp = gparams + (size_t)b * GP_STRIDE;
   const int* gd = gdims + (size_t)b * 4;
   const T* row = tgt + ((size_t)b * m + j) * S;
@@ -164,11 +166,12 @@ __global__ void grid_scan_kernel(const int* __restrict__ cell_count, int cells_s
 }
 
 template <typename T>
-__global__ void grid_scatter_kernel(const T* __restrict__ tgt, int m, int S, int cells_stride, const int* __restrict__ cell_of,
-                                    const int* __restrict__ cell_start, int* __restrict__ cell_cursor, GridRec<T>* __restrict__ recs) {
+__global__ void grid_scatter_kernel(const T* __restrict__ tgt, int m, int S, const int32_t* __restrict__ m_valid, int cells_stride,
+                                    const int* __restrict__ cell_of, const int* __restrict__ cell_start, int* __restrict__ cell_cursor,
+                                    GridRec<T>* __restrict__ recs) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
+  if (j >= (m_valid != nullptr ? min(max(m_valid[b], 1), m) : m)) return;
   const int cell = cell_of[(size_t)b * m + j];
   const int pos = cell_start[(size_t)b * cells_stride + cell] + atomicAdd(&cell_cursor[(size_t)b * cells_stride + cell], 1);
   const T* row = tgt + ((size_t)b * m + j) * S;
@@ -324,26 +327,26 @@ GridWorkspace grid_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, int
 }
 
 template <typename T>
-int grid_build(const T* tgt, int N, int m, int S, const GridWorkspace& g, cudaStream_t st) {
+int grid_build(const T* tgt, int N, int m, int S, const int32_t* m_valid, const GridWorkspace& g, cudaStream_t st) {
   const int cap = grid_cells_cap(m);
   DICP_CUDA(cudaMemsetAsync(g.cell_count, 0, sizeof(int) * (size_t)N * g.cells_stride, st));
   DICP_CUDA(cudaMemsetAsync(g.max_occupancy, 0, sizeof(int), st));
   const char* hs = getenv("DICP_GRID_HSCALE");            // tuning knob (tools/prof_grid.py); default GRID_HSCALE
   const double hscale = hs != nullptr ? atof(hs) : GRID_HSCALE;
-  grid_bbox_kernel<T><<<N, 256, 0, st>>>(tgt, m, S, cap, hscale, g.gparams, g.gdims);
+  grid_bbox_kernel<T><<<N, 256, 0, st>>>(tgt, m, S, m_valid, cap, hscale, g.gparams, g.gdims);
   DICP_LAUNCH_CHECK();
   dim3 grid((m + 255) / 256, N);
-  grid_count_kernel<T><<<grid, 256, 0, st>>>(tgt, m, S, g.cells_stride, g.gparams, g.gdims, g.cell_count, g.cell_of);
+  grid_count_kernel<T><<<grid, 256, 0, st>>>(tgt, m, S, m_valid, g.cells_stride, g.gparams, g.gdims, g.cell_count, g.cell_of);
   DICP_LAUNCH_CHECK();
   grid_scan_kernel<<<N, 1024, 0, st>>>(g.cell_count, g.cells_stride, g.gdims, g.cell_start, g.max_occupancy);
   DICP_LAUNCH_CHECK();
   DICP_CUDA(cudaMemsetAsync(g.cell_count, 0, sizeof(int) * (size_t)N * g.cells_stride, st));
-  grid_scatter_kernel<T><<<grid, 256, 0, st>>>(tgt, m, S, g.cells_stride, g.cell_of, g.cell_start, g.cell_count, (GridRec<T>*)g.recs);
+  grid_scatter_kernel<T><<<grid, 256, 0, st>>>(tgt, m, S, m_valid, g.cells_stride, g.cell_of, g.cell_start, g.cell_count, (GridRec<T>*)g.recs);
   DICP_LAUNCH_CHECK();
   return 0;
 }
-template int grid_build<float>(const float*, int, int, int, const GridWorkspace&, cudaStream_t);
-template int grid_build<double>(const double*, int, int, int, const GridWorkspace&, cudaStream_t);
+template int grid_build<float>(const float*, int, int, int, const int32_t*, const GridWorkspace&, cudaStream_t);
+template int grid_build<double>(const double*, int, int, int, const int32_t*, const GridWorkspace&, cudaStream_t);
 
 // sort the queries by cell (once per call, at their initial position): g.q_order
 template <typename T>
@@ -382,7 +385,7 @@ static int nn_argmin_grid_impl(const T* q, const T* tgt, int N, int n, int m, in
   const GridWorkspace g = grid_ws_layout(ws, ws_bytes, N, n, m, sizeof(T));
   if (ws == nullptr || g.total > ws_bytes) { set_error("dicp_nn_argmin_grid: workspace too small"); return DICP_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = grid_build<T>(tgt, N, m, S, g, st);
+  int rc = grid_build<T>(tgt, N, m, S, nullptr, g, st);
   if (rc) return rc;
   rc = grid_sort_queries<T>(q, nullptr, N, n, g, st);
   if (rc) return rc;

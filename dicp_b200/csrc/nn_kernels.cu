@@ -44,12 +44,14 @@ __device__ __forceinline__ void make_record(float x, float y, float z, float4& v
 __device__ __forceinline__ void make_record(double x, double y, double z, double4& v) { v.x = x; v.y = y; v.z = z; v.w = 0.0; }
 
 template <typename T>
-__global__ void nn_pack_kernel(const T* __restrict__ tgt, int m, int m_pad, int S, typename Vec4<T>::type* __restrict__ packed) {
+__global__ void nn_pack_kernel(const T* __restrict__ tgt, int m, int m_pad, int S, const int32_t* __restrict__ m_valid,
+                               typename Vec4<T>::type* __restrict__ packed) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m_pad) return;
   typename Vec4<T>::type v;
-  if (j < m) {
+  const int mb = m_valid != nullptr ? min(max(m_valid[b], 1), m) : m;      // rows >= m_valid[b] are padding: never a neighbour
+  if (j < mb) {
     const T* row = tgt + ((size_t)b * m + j) * S;
     make_record(row[0], row[1], row[2], v);
   } else {
@@ -59,15 +61,15 @@ __global__ void nn_pack_kernel(const T* __restrict__ tgt, int m, int m_pad, int 
 }
 
 template <typename T>
-int nn_pack_targets(const T* tgt, int N, int m, int S, typename Vec4<T>::type* packed, cudaStream_t st) {
+int nn_pack_targets(const T* tgt, int N, int m, int S, const int32_t* m_valid, typename Vec4<T>::type* packed, cudaStream_t st) {
   const int m_pad = nn_m_pad(m);
   dim3 grid((m_pad + 255) / 256, N);
-  nn_pack_kernel<T><<<grid, 256, 0, st>>>(tgt, m, m_pad, S, packed);
+  nn_pack_kernel<T><<<grid, 256, 0, st>>>(tgt, m, m_pad, S, m_valid, packed);
   DICP_LAUNCH_CHECK();
   return 0;
 }
-template int nn_pack_targets<float>(const float*, int, int, int, float4*, cudaStream_t);
-template int nn_pack_targets<double>(const double*, int, int, int, double4*, cudaStream_t);
+template int nn_pack_targets<float>(const float*, int, int, int, const int32_t*, float4*, cudaStream_t);
+template int nn_pack_targets<double>(const double*, int, int, int, const int32_t*, double4*, cudaStream_t);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -553,7 +555,7 @@ static int nn_argmin_impl(const T* q, const T* tgt, int N, int n, int m, int S, 
   Arena ar(ws, ws_bytes);
   typedef typename Vec4<T>::type V4;
   V4* packed = ar.take<V4>((size_t)N * nn_m_pad(m));
-  int rc = nn_pack_targets<T>(tgt, N, m, S, packed, st);
+  int rc = nn_pack_targets<T>(tgt, N, m, S, nullptr, packed, st);
   if (rc) return rc;
   return nn_search<T>(q, nullptr, packed, N, n, m, idx_out, d2_out, nullptr, (char*)ws + ar.off, ws_bytes - ar.off, st);
 }
@@ -602,11 +604,11 @@ int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, 
 size_t dicp_nn_packed_bytes(int N, int m, int elem_size) { return dicp::nn_packed_bytes(N, m, elem_size); }
 int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream) {
   DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
-  return dicp::nn_pack_targets<float>(tgt, N, m, S, (float4*)packed, (cudaStream_t)stream);
+  return dicp::nn_pack_targets<float>(tgt, N, m, S, nullptr, (float4*)packed, (cudaStream_t)stream);
 }
 int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void* stream) {
   DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
-  return dicp::nn_pack_targets<double>(tgt, N, m, S, (double4*)packed, (cudaStream_t)stream);
+  return dicp::nn_pack_targets<double>(tgt, N, m, S, nullptr, (double4*)packed, (cudaStream_t)stream);
 }
 int dicp_nn_scan_f32(const float* q, const void* packed, int N, int n, int m, int32_t* idx_out, float* d2_out, void* ws,
                      size_t ws_bytes, void* stream) {

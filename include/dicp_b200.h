@@ -125,6 +125,9 @@ DICP_API int dicp_gather_rows_bwd_f64(const double* grad_out, const int32_t* idx
 /* ---- the whole solver loop: replaces dICP/ICP.py:125-303 -------------------------------
  * inputs  source [N,n,3], target [N,m,S] (S=6 for pt2pl, 3 or 6 for pt2pt),
  *         T_init [N,4,4], w_init [N,n] (per point; pt2pt's x3 repeat is implicit)
+ *         m_valid [N] int32 or NULL: number of real rows of every target cloud; rows beyond it
+ *         are padding of a ragged batch (ICP.py:471-479) and are never returned as a neighbour,
+ *         whatever they contain
  * outputs pc [N,n,3], T [N,4,4],
  *         deltas  [N,K,6]        K = max_iterations rows are allocated; the first
  *         weights [N,K,n*R]      *iters_run_host are valid (R = 1 pt2pl, 3 pt2pt)
@@ -136,13 +139,13 @@ DICP_API int dicp_gather_rows_bwd_f64(const double* grad_out, const int32_t* idx
  *         once at its end, and every check_every iterations when !const_iter).          */
 DICP_API size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size);
 DICP_API int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init,
-                         int N, int n, int m, int S, const dicp_params* params,
+                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
                          float* pc, float* T_out, float* deltas, float* weights, float* costs,
                          uint8_t* converged, float* num_iters, float* match_ratio,
                          int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
                          void* ws, size_t ws_bytes, void* stream);
 DICP_API int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init,
-                         int N, int n, int m, int S, const dicp_params* params,
+                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
                          double* pc, double* T_out, double* deltas, double* weights, double* costs,
                          uint8_t* converged, double* num_iters, double* match_ratio,
                          int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,

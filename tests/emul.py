@@ -50,7 +50,7 @@ def forward(source, target, T_init, w_init, params):
     iters = ctypes.c_int32(0)
     fn = getattr(lib, "emul_icp_forward_" + sfx)
     fn.restype = ctypes.c_int
-    rc = fn(_p(source), _p(target), _p(T_init), _p(w_init), N, n, m, S, ctypes.byref(params), _p(out["pc"]), _p(out["T"]),
+    rc = fn(_p(source), _p(target), _p(T_init), _p(w_init), None, N, n, m, S, ctypes.byref(params), _p(out["pc"]), _p(out["T"]),
             _p(out["deltas"]), _p(out["weights"]), _p(out["costs"]), _p(out["converged"]), _p(out["iterations"]),
             _p(out["matched_ratio"]), _p(out["saved_idx"]), _p(out["saved_state"]), ctypes.byref(iters), None,
             ctypes.c_size_t(0), None)

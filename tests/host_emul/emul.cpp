@@ -216,7 +216,8 @@ static int backward(const T* source, const T* target, const T* w_init, int N, in
 extern "C" {
 #define EMUL_FWD(SFX, T)                                                                                                          \
   __attribute__((visibility("default"))) int emul_icp_forward_##SFX(                                                              \
-      const T* source, const T* target, const T* T_init, const T* w_init, int N, int n, int m, int S, const dicp_params* p, T* pc, \
+      const T* source, const T* target, const T* T_init, const T* w_init, const int32_t*, int N, int n, int m, int S,            \
+      const dicp_params* p, T* pc,                                                                                               \
       T* T_out, T* deltas, T* weights, T* costs, uint8_t* converged, T* num_iters, T* match_ratio, int32_t* saved_idx,            \
       double* saved_state, int32_t* iters_run, void*, size_t, void*) {                                                            \
     return forward<T>(source, target, T_init, w_init, N, n, m, S, p, pc, T_out, deltas, weights, costs, converged, num_iters,      \

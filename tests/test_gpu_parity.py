@@ -515,3 +515,20 @@ def test_icp_grid_mode_equals_brute_mode():
     res = icp.icp(sl, tl, torch.eye(4, dtype=torch.float64, device="cuda").repeat(3, 1, 1), trim_dist=5.0,
                   loss_fn={"name": "huber", "metric": 1.0}, dim=2)
     _check(res, g, 1e-9)
+
+
+def test_ragged_targets_use_valid_counts_not_pad_values():
+    """the padding rows of a ragged target batch are excluded by count, so the
+    result no longer depends on max(source) * target_pad_val being far away (it is not when
+    max(source) <= 0, ICP.py:460), and the grid search stays usable for ragged batches."""
+    g = load_golden("ragged_pt2pl")
+    for mode in ("brute", "grid"):
+        for pad_val in (1000, 0.001, -3.0):
+            sl = [tt(g["s1"]).cuda(), tt(g["s2"]).cuda(), tt(g["s3"]).cuda()]
+            tl = [tt(g[k]).cuda() for k in ("t1", "t2", "t3")]
+            icp = _icp("pt2pl", True, 25, 1e-8)
+            icp.nn_search = mode
+            icp.target_pad_val = pad_val
+            res = icp.icp(sl, tl, torch.eye(4, dtype=torch.float64, device="cuda").repeat(3, 1, 1), trim_dist=5.0,
+                          loss_fn={"name": "huber", "metric": 1.0}, dim=2)
+            _check(res, g, 1e-9)
