@@ -229,7 +229,14 @@ grid_query_kernel(const T* __restrict__ q, const double* __restrict__ state, int
   int bi = 0x7fffffff;
   const int rmax = max(max(max(cx, nx - 1 - cx), max(cy, ny - 1 - cy)), max(cz, nz - 1 - cz));
   constexpr int R0 = 1;                       // the 3x3x3 block around the query's cell is visited first, as 9 row runs
+  const int m_recs = cs[gd[3]];               // records of this pair (= valid targets)
   for (int r = R0; r <= max(rmax, R0); ++r) {
+    // a query far from every target (bad initial guess, outlier) would walk O(r^3) empty cells: once
+    // the rows of the next ring outnumber the records, scan the records linearly instead (bounded work)
+    if (r > R0 && (long long)(2 * r + 1) * (2 * r + 1) * 4 > (long long)max(m_recs, 256)) {
+      grid_visit_run<T>(cs, rb, 0, gd[3] - 1, x0, x1, x2, best, bi);
+      break;
+    }
     const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
     const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
     const int xa = max(cx - r, 0), xb = min(cx + r, nx - 1);

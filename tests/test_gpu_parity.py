@@ -481,6 +481,8 @@ def test_grid_nn_equals_brute_surface_duplicates_outliers():
     far = src.clone()
     far[:, :7] += 500.0                                            # queries far outside the grid
     _grid_equals_brute(far, tgt)
+    _grid_equals_brute(src + 30.0, tgt)                            # every query far from every target (linear-scan cap)
+    _grid_equals_brute(src + torch.tensor([0.0, 0.0, 6.0]), tgt)   # all queries a few cells above the surface
     flat = tgt.clone()
     flat[:, :, 2] = 0.0                                            # planar target (zero z extent)
     _grid_equals_brute(src, flat)
