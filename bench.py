@@ -192,7 +192,9 @@ def roofline_nn(src, tgt, pk):
     ach = flop / sec / 1e12
     executed = 6.0 * evals / sec / 1e12      # what the filter scan issues: 3 FFMA per evaluation (refine + fallback < 2 % more)
     return {"kernel": "nn_scan_f32_kernel<8> + exact fallback (one dicp_nn_scan_f32 call)", "bound": "fp32",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms_per_launch": sec * 1e3,
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of nn_scan_f32_kernel<8> at these shapes (profiles/r01_ncu_full_top_kernels.md)
+            "traffic": 130.9e6 if (N, n, m) == (256, 16384, 16384) else None, "ms_per_launch": sec * 1e3,
             "executed_tflops": executed, "frac_executed": executed / peak,
             "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],
             "flop_per_pair_eval": {"algorithmic": 8, "executed": 6}, "units_per_launch": evals}, idx
@@ -220,7 +222,9 @@ def roofline_gn(src, tgt, idx, pk):
     nbytes = 48.0 * N * n                    # p 12 + gathered (q,n) 24 + idx 4 + w_init 4 + weights write 4
     ach = nbytes / sec / 1e9
     return {"kernel": "gn_accum_kernel<float,pt2pl,3> (one dicp_gn_accumulate_f32 call: + 2 tiny launches)", "bound": "hbm",
-            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            # dram bytes of gn_accum_kernel at 256 pairs from the same ncu capture: 184.6 MB read + 15.7 MB written
+            "traffic": 200.3e6 if (N, n, m) == (256, 16384, 16384) else None,
             "ms_per_launch": sec * 1e3, "peak_source": pk["source"], "bytes_per_correspondence": 48,
             "units_per_launch": float(N) * n, "pairs": N}
 
