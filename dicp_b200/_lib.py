@@ -9,7 +9,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdicp_b200.so")
+LIB_PATH = os.environ.get("DICP_B200_LIB", os.path.join(_HERE, "lib", "libdicp_b200.so"))
 
 DICP_PT2PL, DICP_PT2PT = 0, 1
 LOSS_IDS = {None: 0, "huber": 1, "cauchy": 2}

@@ -66,11 +66,17 @@ __device__ __forceinline__ void block_reduce_store(const T* vals, double* out, d
 }
 
 template <typename T> struct GnUnroll;
-template <> struct GnUnroll<float> { static constexpr int U = 4; };
+#ifndef GN_U
+#define GN_U 4
+#endif
+template <> struct GnUnroll<float> { static constexpr int U = GN_U; };
 template <> struct GnUnroll<double> { static constexpr int U = 2; };
 
+#ifndef GN_MINB
+#define GN_MINB 1
+#endif
 template <typename T, bool PT2PL, int DIM>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, GN_MINB)
 gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
                 const int32_t* __restrict__ idx, const double* __restrict__ state, int n, int m, int S,
                 WeightParams P, T* __restrict__ weights_out, long long w_pair_stride,

@@ -24,15 +24,13 @@
 
 namespace dicp {
 
-constexpr int GP_ORIGIN = 0;    // 3 floats
-constexpr int GP_H = 3;         // cell size
+// per-pair grid parameters (doubles): origin xyz, cell size h, 1/h; the dims live in gdims[b] = {nx, ny, nz, ncells}
+constexpr int GP_ORIGIN = 0;
+constexpr int GP_H = 3;
 constexpr int GP_INVH = 4;
-constexpr int GP_DIMS = 5;      // 3 ints (stored as float bits via int array alias below)
 constexpr int GP_STRIDE = 8;
 
-template <typename T> struct GridRec { T x, y, z; int idx; };
-
-struct GridDims { int nx, ny, nz; };
+template <typename T> struct GridRec { T x, y, z; int idx; };   // 16 B (fp32) / 32 B (fp64): one load per candidate
 
 template <typename T>
 __global__ void grid_bbox_kernel(const T* __restrict__ tgt, int m_all, int S, const int32_t* __restrict__ m_valid, int cells_cap,

@@ -25,6 +25,24 @@ def timed(fn, reps=5, warm=2):
 
 
 out = {}
+# config 1: the reference's pytest fixture, fp64, pt2pl + Cauchy, dim 2, tol 1e-10 (7 iterations), forward + backward
+import numpy as np
+fx = np.load(os.path.join(ROOT, "tests", "golden", "fixture_clouds.npz"))
+s1 = torch.tensor(fx["scan"][:, :3]).cuda().requires_grad_(True)
+t1 = torch.tensor(fx["map"]).cuda().requires_grad_(True)
+icp1 = ICP(icp_type="pt2pl", max_iterations=100, tolerance=1e-10)
+
+
+def step1():
+    s1.grad = t1.grad = None
+    r = icp1.icp(s1, t1, torch.eye(4, dtype=torch.float64, device="cuda"), trim_dist=5.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=2)
+    r["T"].sum().backward()
+    return r
+
+
+ms = timed(step1, reps=20, warm=3)
+out["config1_fixture_65pts_fp64_fwd_bwd"] = {"ms": ms, "iterations": int(step1()["stats"]["iterations"][0])}
+
 src, tgt = make_wavy_pair(64, 4096, 4096, seed=2000, dtype=torch.float32, with_normals=False)
 src, tgt, T0 = src.cuda(), tgt.cuda(), torch.eye(4, device="cuda").repeat(64, 1, 1)
 icp = ICP(icp_type="pt2pt", max_iterations=10, tolerance=1e-12)
