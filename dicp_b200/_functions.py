@@ -72,6 +72,54 @@ class GatherRows(torch.autograd.Function):
         return gy, None
 
 
+class GumbelNN(torch.autograd.Function):
+    """Streaming Gumbel-softmax soft nearest neighbour (nn.py:43-70): x (N,n,3), y (N,m,S) -> (N,n,S).
+    The noise is a pure function of (seed, pair, query, target), so the backward regenerates it."""
+
+    @staticmethod
+    def forward(ctx, x, y, seed, eps, tau):
+        lib = load_library()
+        x, y = x.contiguous(), y.contiguous()
+        N, n, _ = x.shape
+        m, S = y.shape[1], y.shape[2]
+        sfx = suffix(x.dtype)
+        out = torch.empty((N, n, S), dtype=x.dtype, device=x.device)
+        lse = torch.empty((N, n), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = getattr(lib, "dicp_gumbel_nn_" + sfx)(ptr(x), ptr(y), N, n, m, S, int(seed), float(eps), float(tau), ptr(out), ptr(lse),
+                                                       stream_ptr(x.device))
+        check(rc, "dicp_gumbel_nn_" + sfx)
+        ctx.save_for_backward(x, y, out, lse)
+        ctx.cfg = (int(seed), float(eps), float(tau))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = load_library()
+        x, y, out, lse = ctx.saved_tensors
+        seed, eps, tau = ctx.cfg
+        N, n, _ = x.shape
+        m, S = y.shape[1], y.shape[2]
+        sfx = suffix(x.dtype)
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        scratch = torch.empty((N, n), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = getattr(lib, "dicp_gumbel_nn_bwd_" + sfx)(ptr(x), ptr(y), ptr(out), ptr(lse), ptr(g.contiguous()), N, n, m, S, seed, eps, tau,
+                                                           ptr(gx), ptr(gy), ptr(scratch), stream_ptr(x.device))
+        check(rc, "dicp_gumbel_nn_bwd_" + sfx)
+        return gx, gy, None, None, None
+
+
+def gumbel_noise(N, n, m, seed, eps, dtype, device):
+    """The noise tensor G (N,n,m) GumbelNN uses for `seed` (tests)."""
+    lib = load_library()
+    G = torch.empty((N, n, m), dtype=dtype, device=device)
+    with torch.cuda.device(device):
+        rc = getattr(lib, "dicp_gumbel_noise_" + suffix(dtype))(N, n, m, int(seed), float(eps), ptr(G), stream_ptr(device))
+    check(rc, "dicp_gumbel_noise")
+    return G
+
+
 class KabschSums(torch.autograd.Function):
     """sums[b] = (sum p, sum q, sum q p^T) over the correspondences q_i = y[b, idx[b,i], :3]
     (ICP.py:557-563 without the O(1) 3x3 part).  x (N,n,3), y (N,m,S), idx (N,n) int32 -> (N,16)."""

@@ -31,6 +31,7 @@ class DicpParams(ctypes.Structure):
 _lib = None
 _lock = threading.Lock()
 _P, _I, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+_U64, _D = ctypes.c_ulonglong, ctypes.c_double
 
 _SIGNATURES = {
     "dicp_version": ([], ctypes.c_int),
@@ -55,6 +56,9 @@ for _s in ("f32", "f64"):
                                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_kabsch_sums_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_kabsch_sums_bwd_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I)
+    _SIGNATURES["dicp_gumbel_nn_" + _s] = ([_P, _P, _I, _I, _I, _I, _U64, _D, _D, _P, _P, _P], _I)
+    _SIGNATURES["dicp_gumbel_nn_bwd_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _U64, _D, _D, _P, _P, _P, _P], _I)
+    _SIGNATURES["dicp_gumbel_noise_" + _s] = ([_I, _I, _I, _U64, _D, _P, _P], _I)
     _SIGNATURES["dicp_gn_accumulate_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams),
                                                _P, _P, _P, _Z, _P], _I)
 

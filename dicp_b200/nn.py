@@ -7,8 +7,11 @@ into y — the same gradient path the reference has (nn.py:37-38).  Inputs on th
 staged through the GPU; without a GPU this raises (no CPU fallback).
 
 The Gumbel-softmax variant (nn.py:43-70, "not yet integrated" upstream, off in the shipped
-config, RNG-dependent so it has no parity definition) is outside the kernel scope and is
-kept as plain tensor math so that the constructor default `use_gumbel=True` still works."""
+config; the constructor default `use_gumbel=True` selects it) runs as a streaming online-softmax
+kernel (`dicp_gumbel_nn_*`, O(n+m) memory instead of the reference's dense (N,n,m) tensor) with
+a counter-based noise generator seeded from torch's default generator, so `torch.manual_seed`
+makes it reproducible.  It is a different random stream than `torch.rand`, hence parity is
+defined against the same formula evaluated on the kernel's own noise (tests)."""
 import torch
 
 from . import _functions
@@ -40,13 +43,18 @@ class nn:
         out = _functions.GatherRows.apply(y, idx)
         return out if out.device == dev else out.to(dev)
 
-    # -- Gumbel-softmax NN (nn.py:43-70), out of kernel scope ---------------------------
+    # -- Gumbel-softmax NN (nn.py:43-70): streaming kernel --------------------------------
     def _soft_nn(self, x, y):
-        d2 = ((x.unsqueeze(2) - y.unsqueeze(1)[..., :3]) ** 2).sum(dim=3)
-        u = torch.rand(d2.shape, device=d2.device)
-        gumbel = -torch.log(-torch.log(u + self.eps) + self.eps)
-        probs = torch.softmax((gumbel - d2) / self.tau, dim=2)
-        return probs @ y
+        dev = x.device
+        if not x.is_cuda:
+            _functions.require_cuda()
+            x, y = x.cuda(), y.cuda()
+        if y.dtype != x.dtype:
+            y = y.to(x.dtype)
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())      # torch.manual_seed controls it
+        self.last_seed = seed
+        out = _functions.GumbelNN.apply(x, y, seed, self.eps, self.tau)
+        return out if out.device == dev else out.to(dev)
 
     # -- layout normalisation (nn.py:94-125) --------------------------------------------
     @staticmethod

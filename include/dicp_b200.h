@@ -195,6 +195,25 @@ DICP_API int dicp_kabsch_sums_bwd_f32(const float* source, const float* target, 
 DICP_API int dicp_kabsch_sums_bwd_f64(const double* source, const double* target, const int32_t* idx, int N, int n, int m, int S,
                              const double* grad_sums, double* grad_source, double* grad_target, void* stream);
 
+/* ---- Gumbel-softmax soft nearest neighbour: replaces dICP/nn.py:43-70 ----------------------
+ * out[b,i,:] = sum_j softmax_j((-|x_i - y_j|^2 + G_ij) / tau) y[b,j,:],  G = -log(-log(U+eps)+eps)
+ * streamed with an online softmax (no (N,n,m) tensor); U comes from Philox4x32-10 keyed by `seed`
+ * with counter (pair, query, target/4), so a call is reproducible and the backward regenerates
+ * the same noise.  lse [N,n] (log-sum-exp of the logits) is saved for the backward; ws_n is an
+ * [N,n] scratch array.  dicp_gumbel_noise_* writes the noise tensor itself (tests only).         */
+DICP_API int dicp_gumbel_nn_f32(const float* x, const float* y, int N, int n, int m, int S, unsigned long long seed,
+                       double eps, double tau, float* out, float* lse, void* stream);
+DICP_API int dicp_gumbel_nn_f64(const double* x, const double* y, int N, int n, int m, int S, unsigned long long seed,
+                       double eps, double tau, double* out, double* lse, void* stream);
+DICP_API int dicp_gumbel_nn_bwd_f32(const float* x, const float* y, const float* out, const float* lse, const float* grad_out,
+                           int N, int n, int m, int S, unsigned long long seed, double eps, double tau,
+                           float* grad_x, float* grad_y, float* ws_n, void* stream);
+DICP_API int dicp_gumbel_nn_bwd_f64(const double* x, const double* y, const double* out, const double* lse, const double* grad_out,
+                           int N, int n, int m, int S, unsigned long long seed, double eps, double tau,
+                           double* grad_x, double* grad_y, double* ws_n, void* stream);
+DICP_API int dicp_gumbel_noise_f32(int N, int n, int m, unsigned long long seed, double eps, float* G, void* stream);
+DICP_API int dicp_gumbel_noise_f64(int N, int n, int m, unsigned long long seed, double eps, double* G, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -534,3 +534,54 @@ def test_ragged_targets_use_valid_counts_not_pad_values():
             res = icp.icp(sl, tl, torch.eye(4, dtype=torch.float64, device="cuda").repeat(3, 1, 1), trim_dist=5.0,
                           loss_fn={"name": "huber", "metric": 1.0}, dim=2)
             _check(res, g, 1e-9)
+
+
+# ---------------------------------------------------------------------------------------
+# Gumbel-softmax soft NN (nn.py:43-70) as a streaming kernel
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-4)])
+@pytest.mark.parametrize("S", [3, 6])
+def test_gumbel_nn_matches_formula_on_its_own_noise(dtype, tol, S):
+    """Same formula as the reference (nn.py:58-68) evaluated densely in fp64 on the kernel's noise."""
+    from dicp_b200 import _functions
+    gen = torch.Generator().manual_seed(4)
+    N, n, m, seed, eps, tau = 2, 70, 301, 12345, 1e-10, 0.1
+    x = torch.randn((N, n, 3), generator=gen, dtype=torch.float64).to(dtype).cuda().requires_grad_(True)
+    y = torch.randn((N, m, S), generator=gen, dtype=torch.float64).to(dtype).cuda().requires_grad_(True)
+    out = _functions.GumbelNN.apply(x, y, seed, eps, tau)
+    gw = torch.randn(out.shape, generator=gen, dtype=torch.float64).to(dtype).cuda()
+    (out * gw).sum().backward()
+    G = _functions.gumbel_noise(N, n, m, seed, eps, dtype, x.device).double()
+    xr = x.detach().double().requires_grad_(True)
+    yr = y.detach().double().requires_grad_(True)
+    d2 = ((xr.unsqueeze(2) - yr.unsqueeze(1)[..., :3]) ** 2).sum(dim=3)
+    ref = torch.softmax((G - d2) / tau, dim=2) @ yr
+    (ref * gw.double()).sum().backward()
+    assert rel_err(out.detach().cpu(), ref.detach().cpu()) < tol
+    assert rel_err(x.grad.cpu(), xr.grad.cpu()) < 20 * tol
+    assert rel_err(y.grad.cpu(), yr.grad.cpu()) < 20 * tol
+    # the noise is standard Gumbel: mean = Euler-Mascheroni, variance = pi^2 / 6
+    assert abs(G.mean().item() - 0.5772) < 0.02 and abs(G.var().item() - 1.6449) < 0.06
+
+
+def test_gumbel_nn_default_constructor_reference_test():
+    """tests/test_nn.py:12-41 verbatim semantics: default nn() is the Gumbel path; tau = 0.1 makes the
+    soft neighbour equal the hard one on this point set; gradients reach query and points."""
+    from dICP.nn import nn
+    torch.manual_seed(0)
+    pts = torch.tensor([(5.0, 4.0, 0.0), (2.0, 6.0, 0.0), (13.0, 3.0, 0.0), (8.0, 7.0, 0.0), (3.0, 1.0, 0.0)], requires_grad=True)
+    q = torch.tensor([[9.0, 4.0, 0.0]], requires_grad=True)
+    soft = nn(differentiable=True)
+    for _ in range(10):
+        out = soft.find_nn(q, pts)
+        assert torch.all(out == torch.tensor((8.0, 7.0, 0.0)))
+    out.sum().backward()
+    assert q.grad is not None and pts.grad is not None
+    assert not torch.isnan(q.grad).any() and not torch.isnan(pts.grad).any()
+    pts2 = torch.cat((pts, torch.tensor((10.0, 2.0, 0.0)).view(1, -1)))
+    assert torch.all(soft.find_nn(q, pts2) == torch.tensor((10.0, 2.0, 0.0)))
+    torch.manual_seed(7)
+    a = soft.find_nn(torch.randn(3, 50, 3), torch.randn(3, 60, 6))
+    torch.manual_seed(7)
+    b = soft.find_nn(torch.randn(3, 50, 3), torch.randn(3, 60, 6))
+    assert torch.equal(a, b)            # reproducible under torch.manual_seed
