@@ -121,15 +121,25 @@ gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, cons
     for (int u = 0; u < U; ++u) {
       load_target_row<T, PT2PL>(tgt_b + (size_t)jj[u] * S, S, q[u], nr[u]);
     }
+    // branch-free over the U correspondences so that their long dependent chains (sqrt, tanh, div)
+    // interleave; lanes past the end of the cloud evaluate a clamped copy and are masked out
+    PointEval<T> s[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (ii[u] < 0) continue;
-      PointEval<T> s;
-      eval_point<T, PT2PL>(C, r, p[u], q[u], nr[u], w0[u], P, s);
-      accum_point<T, PT2PL, DIM>(acc, s, w0[u], (T)P.thresh);
-      if (wout != nullptr) {
+    for (int u = 0; u < U; ++u) eval_point<T, PT2PL>(C, r, p[u], q[u], nr[u], w0[u], P, s[u]);
+    if (base + GN_THREADS * U <= n) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) wout[(size_t)ii[u] * R + k] = s.w;                      // ICP.py:222, 164-165
+      for (int u = 0; u < U; ++u) accum_point<T, PT2PL, DIM>(acc, s[u], w0[u], (T)P.thresh);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ii[u] >= 0) accum_point<T, PT2PL, DIM>(acc, s[u], w0[u], (T)P.thresh);
+    }
+    if (wout != nullptr) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ii[u] < 0) continue;
+#pragma unroll
+        for (int k = 0; k < R; ++k) wout[(size_t)ii[u] * R + k] = s[u].w;                   // ICP.py:222, 164-165
       }
     }
   }

@@ -18,3 +18,6 @@ src, tgt = src.cuda().repeat(rep, 1, 1)[:N].contiguous(), tgt.cuda().repeat(rep,
 idx = _functions.nn_argmin(src, tgt, search="grid")
 r = bench.roofline_gn(src, tgt, idx, pk)
 print("gn_accumulate: %.1f us per call, %.0f GB/s, %.1f %% of measured HBM peak" % (r["ms_per_launch"] * 1e3, r["achieved"], 100 * r["frac"]))
+ar = torch.arange(src.shape[1], dtype=torch.int32, device="cuda").repeat(N, 1).contiguous()
+r = bench.roofline_gn(src, tgt, ar, pk)
+print("  with idx = identity (sequential gather): %.1f us, %.0f GB/s" % (r["ms_per_launch"] * 1e3, r["achieved"]))
