@@ -270,17 +270,15 @@ def run_ours(args):
     theta_h = torch.arange(1, 13, dtype=torch.float32).requires_grad_(True)
 
     def step_e2e():
-        """public API with pinned HOST buffers: H2D of the clouds + D2H of T, loss, dloss/dtheta every step."""
+        """public API with pinned HOST buffers: `icp.icp` stages the clouds through the GPU (H2D inside the call),
+        T comes back to the host, the loss and d loss / d theta are evaluated there (D2H of T, H2D of its gradient)."""
         theta_h.grad = None
-        s = src_h.to(dev, non_blocking=True).requires_grad_(True)
-        t = tgt_h.to(dev, non_blocking=True).requires_grad_(True)
-        T0 = T0_h.to(dev, non_blocking=True)
-        res = icp.icp(s, t, T0, trim_dist=TRIM, loss_fn=LOSS, dim=3)
-        th = theta_h.to(dev)
-        loss = learning_loss(res, th)
+        res = icp.icp(src_h, tgt_h, T0_h, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        assert res["T"].device.type == "cpu"
+        loss = learning_loss(res, theta_h)
         loss.backward()
-        out = allreduce(torch.cat((loss.detach().reshape(1), theta_h.grad.to(dev))))
-        return out.cpu(), res["T"].detach().cpu()
+        out = allreduce(torch.cat((loss.detach().reshape(1), theta_h.grad)).to(dev))
+        return out.cpu(), res["T"].detach()
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -341,8 +339,10 @@ def run_ours(args):
         # kernels of libdicp_b200.so per step: forward init + pack + 10 x (scan, merge, fallback, unpack, gn, update) + finalize,
         # backward seed + 10 x (pair, points) + finish
         launches_per_step = (2 + 6 * ITERS + 1) + (1 + 2 * ITERS + 1)
-        h2d = src_h.numel() * 4 + tgt_h.numel() * 4 + T0_h.numel() * 4 + 12 * 4
-        d2h = 13 * 4 + PAIRS_PER_GPU * 16 * 4
+        # per step: clouds + T_init up, the gradient of T up for the backward; T, the stats and the reduced
+        # [loss, dloss/dtheta] down (pc / weights / deltas / costs stay on the GPU until somebody reads them)
+        h2d = (src_h.numel() + tgt_h.numel() + T0_h.numel() + PAIRS_PER_GPU * 16 + 13) * 4
+        d2h = (PAIRS_PER_GPU * (16 + 3) + 13) * 4
         line = {
             "metric": METRIC, "value": pairs_total * args.steps / sec, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",

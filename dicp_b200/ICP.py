@@ -21,6 +21,39 @@ def _is_empty(x):
     return x is None or len(x) == 0
 
 
+class _Results(dict):
+    """The result dictionary of `ICP.icp` (ICP.py:294-303).  When the inputs were host tensors the outputs
+    are produced on the GPU; each entry is copied back to the host the first time it is read, so a caller
+    that only wants `T` does not pay for the (N,K,n,1) `weights` history."""
+
+    def _force(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _Deferred):
+            v = v()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def __getitem__(self, key):
+        return self._force(key)
+
+    def get(self, key, default=None):
+        return self._force(key) if key in self else default
+
+    def items(self):
+        return [(k, self._force(k)) for k in self.keys()]
+
+    def values(self):
+        return [self._force(k) for k in self.keys()]
+
+
+class _Deferred:
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self):
+        return self.fn()
+
+
 class ICP:
     def __init__(self, config_path=None, icp_type='pt2pl', max_iterations=100, tolerance=1e-12, differentiable=True):
         if config_path is None:
@@ -67,6 +100,8 @@ class ICP:
         m_valid = None
         if isinstance(target, list) and len(target) > 0 and not _is_empty(source):
             m_valid = [max(len(t_i), 1) for t_i in target]
+        default_prior = (weight is None and not self.source_zeroes_are_pad and not isinstance(source, list)
+                         and not isinstance(target, list) and not _is_empty(source) and not _is_empty(target))
         source, target, T_init, w_init = self.batch_size_handling(source, target, T_init, weight)
         assert source.dtype == target.dtype == T_init.dtype
         N, n = source.shape[0], source.shape[1]
@@ -89,8 +124,11 @@ class ICP:
             else:
                 target = torch.cat((target[:, :, :2], zt), dim=2)
 
-        # per-point prior weights; pt2pt carries them x3-repeated (ICP.py:508-509)
+        # per-point prior weights; pt2pt carries them x3-repeated (ICP.py:508-509).  The all-ones default of a
+        # dense call is not materialised on the device (the kernels treat a missing prior as 1)
         w_point = w_init if pt2pl else w_init[:, ::3]
+        if default_prior:
+            w_point = None
 
         out_dev = source.device
         dev = self._compute_device(out_dev)
@@ -105,22 +143,29 @@ class ICP:
             m_valid = None                                   # nothing is padded
         if m_valid is not None:
             m_valid = torch.tensor(m_valid, dtype=torch.int32, device=dev)
+        # host buffers are staged through the GPU; from pinned memory the copies are asynchronous and
+        # stream-ordered in front of the kernels
         pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
-            source.to(dev), target.to(dev), T_init.to(dev), w_point.to(dev), params, m_valid)
+            source.to(dev, non_blocking=True), target.to(dev, non_blocking=True), T_init.to(dev, non_blocking=True),
+            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid)
 
         if self.verbose:
             print("ICP converged in {} iterations".format(deltas.shape[1]))
             print("Final del_T_ts: {}".format(torch.linalg.norm(deltas[:, -1])))
 
-        back = (lambda t: t) if out_dev == dev else (lambda t: t.to(out_dev))
-        return {
-            "pc": back(pc),
+        if out_dev == dev:
+            return {"pc": pc, "T": T, "costs": costs.unsqueeze(-1), "deltas": deltas.unsqueeze(-1),
+                    "weights": weights.unsqueeze(-1),
+                    "stats": {"converged": converged, "iterations": num_iters, "matched_ratio": match_ratio}}
+        back = lambda t: t.to(out_dev)      # noqa: E731
+        return _Results({
+            "pc": _Deferred(lambda: back(pc)),
             "T": back(T),
-            "costs": back(costs).unsqueeze(-1),
-            "deltas": back(deltas).unsqueeze(-1),
-            "weights": back(weights).unsqueeze(-1),
+            "costs": _Deferred(lambda: back(costs).unsqueeze(-1)),
+            "deltas": _Deferred(lambda: back(deltas).unsqueeze(-1)),
+            "weights": _Deferred(lambda: back(weights).unsqueeze(-1)),
             "stats": {"converged": back(converged), "iterations": back(num_iters), "matched_ratio": back(match_ratio)},
-        }
+        })
 
     def _compute_device(self, input_device):
         _functions.require_cuda()
