@@ -585,3 +585,50 @@ def test_gumbel_nn_default_constructor_reference_test():
     torch.manual_seed(7)
     b = soft.find_nn(torch.randn(3, 50, 3), torch.randn(3, 60, 6))
     assert torch.equal(a, b)            # reproducible under torch.manual_seed
+
+
+# ---------------------------------------------------------------------------------------
+# gradients of the CUDA path against central finite differences of the CUDA forward itself
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
+def test_backward_matches_finite_differences(icp_type):
+    """Independent of the oracle: d loss / d input from the hand-written backward kernels equals the central
+    difference of the CUDA forward (fp64, 3 constant iterations, well separated clouds so that the
+    correspondences do not change under the 1e-6 perturbations)."""
+    gen = torch.Generator().manual_seed(17)
+    N, n, m = 2, 24, 30
+    tgt_xyz = torch.rand((N, m, 3), generator=gen, dtype=torch.float64) * 10
+    nrm = torch.randn((N, m, 3), generator=gen, dtype=torch.float64)
+    nrm = nrm / nrm.norm(dim=-1, keepdim=True)
+    tgt = torch.cat((tgt_xyz, nrm), dim=-1) if icp_type == "pt2pl" else tgt_xyz
+    src = tgt_xyz[:, torch.randperm(m, generator=gen)[:n]] + 0.05 * torch.randn((N, n, 3), generator=gen, dtype=torch.float64)
+    w = 0.5 + torch.rand((N, n), generator=gen, dtype=torch.float64)
+    T0 = torch.eye(4, dtype=torch.float64).repeat(N, 1, 1)
+    T0[:, :3, 3] = torch.tensor([0.02, -0.01, 0.03], dtype=torch.float64)
+    gT = torch.randn((N, 4, 4), generator=gen, dtype=torch.float64).cuda()
+    gT[:, 3, :] = 0
+    gp = (0.1 * torch.randn((N, n, 3), generator=gen, dtype=torch.float64)).cuda()
+    icp = _icp(icp_type, True, 3, 1e-14, const_iter=True)
+
+    def loss_of(s, t, ww, TT):
+        res = icp.icp(s, t, TT, weight=ww, trim_dist=1.5, loss_fn={"name": "cauchy", "metric": 0.3}, dim=3)
+        return (res["T"] * gT).sum() + (res["pc"] * gp).sum()
+
+    leaves = [x.cuda().requires_grad_(True) for x in (src, tgt, w, T0)]
+    loss_of(*leaves).backward()
+    eps = 1e-6
+    for li, leaf in enumerate(leaves):
+        flat = leaf.detach().reshape(-1)
+        picks = torch.randperm(flat.numel(), generator=gen)[:6].tolist()
+        if li == 3:
+            picks = [p for p in picks if (p % 16) < 12] or [3]          # the bottom row of T_init is not used
+        for pidx in picks:
+            vals = []
+            for sgn in (+1.0, -1.0):
+                pert = [x.detach().clone() for x in leaves]
+                pert[li].reshape(-1)[pidx] += sgn * eps
+                with torch.no_grad():
+                    vals.append(float(loss_of(*pert)))
+            fd = (vals[0] - vals[1]) / (2 * eps)
+            an = float(leaf.grad.reshape(-1)[pidx])
+            assert abs(fd - an) <= 2e-6 * max(1.0, abs(fd), abs(an)), (li, pidx, fd, an)
