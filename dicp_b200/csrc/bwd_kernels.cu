@@ -112,7 +112,7 @@ __global__ void bwd_pair_kernel(const double* __restrict__ partials, int nblk, c
   bw[BW_ACTIVE] = active;
 }
 
-template <typename T, bool PT2PL>
+template <typename T, bool PT2PL, bool FASTW>
 __global__ void __launch_bounds__(BW_THREADS)
 bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
                   const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
@@ -161,7 +161,7 @@ bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, co
         if (ii[u] < 0) continue;
         const int i = ii[u];
         PointEval<T> s;
-        eval_point<T, PT2PL>(C, r, p[u], q[u], nr[u], w0[u], P, s);
+        eval_point<T, PT2PL, FASTW>(C, r, p[u], q[u], nr[u], w0[u], P, s);
         T abar[3], ebar[3], nbar[3], w0bar;
         point_backward<T, PT2PL>(s, w0[u], lam, del, abar, ebar, nbar, w0bar);
         if (grad_w != nullptr) grad_w[(size_t)b * n + i] += w0bar;
@@ -202,6 +202,7 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
   cudaStream_t st = (cudaStream_t)stream;
   IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T));
   const WeightParams P = make_weight_params(p);
+  const bool fast = weight_params_fast(P);
   const int nblk = bw_blocks_per_pair(n);
   const size_t rec_stride = (size_t)N * ST_STRIDE;
   const bool pl = p->icp_type == DICP_PT2PL;
@@ -217,8 +218,13 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
     bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, nblk, rec_k, p->dim, k == iters_run - 1 ? 0 : 1, grad_T, w.bw_state, grad_T_init, N);
     DICP_LAUNCH_CHECK();
     const int32_t* idx_k = saved_idx + (size_t)k * N * n;
-    if (pl) bwd_points_kernel<T, true><<<pgrid, BW_THREADS, 0, st>>>(source, target, w_init, idx_k, rec_k, w.bw_state, n, m, S, P, grad_source, grad_target, grad_w, w.bw_partials);
-    else bwd_points_kernel<T, false><<<pgrid, BW_THREADS, 0, st>>>(source, target, w_init, idx_k, rec_k, w.bw_state, n, m, S, P, grad_source, grad_target, grad_w, w.bw_partials);
+#define DICP_BW_LAUNCH(PL, FW) \
+  bwd_points_kernel<T, PL, FW><<<pgrid, BW_THREADS, 0, st>>>(source, target, w_init, idx_k, rec_k, w.bw_state, n, m, S, P, grad_source, grad_target, grad_w, w.bw_partials)
+    if (pl && fast) DICP_BW_LAUNCH(true, true);
+    else if (pl) DICP_BW_LAUNCH(true, false);
+    else if (fast) DICP_BW_LAUNCH(false, true);
+    else DICP_BW_LAUNCH(false, false);
+#undef DICP_BW_LAUNCH
     DICP_LAUNCH_CHECK();
   }
   bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, nblk, saved_state, p->dim, 2, grad_T, w.bw_state, grad_T_init, N);

@@ -75,7 +75,7 @@ template <> struct GnUnroll<double> { static constexpr int U = 2; };
 #ifndef GN_MINB
 #define GN_MINB 1
 #endif
-template <typename T, bool PT2PL, int DIM>
+template <typename T, bool PT2PL, int DIM, bool FASTW>
 __global__ void __launch_bounds__(GN_THREADS, GN_MINB)
 gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
                 const int32_t* __restrict__ idx, const double* __restrict__ state, int n, int m, int S,
@@ -125,7 +125,7 @@ gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, cons
     // interleave; lanes past the end of the cloud evaluate a clamped copy and are masked out
     PointEval<T> s[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) eval_point<T, PT2PL>(C, r, p[u], q[u], nr[u], w0[u], P, s[u]);
+    for (int u = 0; u < U; ++u) eval_point<T, PT2PL, FASTW>(C, r, p[u], q[u], nr[u], w0[u], P, s[u]);
     if (base + GN_THREADS * U <= n) {
 #pragma unroll
       for (int u = 0; u < U; ++u) accum_point<T, PT2PL, DIM>(acc, s[u], w0[u], (T)P.thresh);
@@ -153,8 +153,14 @@ int gn_accumulate(const T* source, const T* target, const T* w_init, const int32
   const WeightParams P = make_weight_params(p);
   dim3 grid(gn_blocks_per_pair(n), N);
   const bool pl = p->icp_type == DICP_PT2PL;
-#define DICP_GN_LAUNCH(PL, DM) \
-  gn_accum_kernel<T, PL, DM><<<grid, GN_THREADS, 0, st>>>(source, target, w_init, idx, state, n, m, S, P, weights_out, w_pair_stride, partials, stop_flag)
+  const bool fast = weight_params_fast(P);
+#define DICP_GN_LAUNCH(PL, DM)                                                                                                          \
+  do {                                                                                                                                  \
+    if (fast) gn_accum_kernel<T, PL, DM, true><<<grid, GN_THREADS, 0, st>>>(source, target, w_init, idx, state, n, m, S, P, weights_out, \
+                                                                            w_pair_stride, partials, stop_flag);                        \
+    else gn_accum_kernel<T, PL, DM, false><<<grid, GN_THREADS, 0, st>>>(source, target, w_init, idx, state, n, m, S, P, weights_out,     \
+                                                                        w_pair_stride, partials, stop_flag);                            \
+  } while (0)
   if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
   else if (pl) DICP_GN_LAUNCH(true, 2);
   else if (p->dim == 3) DICP_GN_LAUNCH(false, 3);
