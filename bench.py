@@ -194,7 +194,7 @@ def roofline_nn(src, tgt, pk):
     return {"kernel": "nn_scan_f32_kernel<8> + exact fallback (one dicp_nn_scan_f32 call)", "bound": "fp32",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of nn_scan_f32_kernel<8> at these shapes (profiles/r01_ncu_full_top_kernels.md)
-            "traffic": 130.9e6 if (N, n, m) == (256, 16384, 16384) else None, "ms_per_launch": sec * 1e3,
+            "traffic": 132.2e6 if (N, n, m) == (256, 16384, 16384) else None, "ms_per_launch": sec * 1e3,
             "executed_tflops": executed, "frac_executed": executed / peak,
             "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],
             "flop_per_pair_eval": {"algorithmic": 8, "executed": 6}, "units_per_launch": evals}, idx

@@ -104,14 +104,17 @@ struct Ctrl {
 // ---- nearest neighbour (nn_kernels.cu) ------------------------------------------------
 size_t nn_workspace_bytes(int N, int n, int m, int elem_size);
 // packed targets: [N, m_pad] records, m_pad = round_up(m, NN_CHUNK), sentinel rows.
-//   float : (-2x,-2y,-2z,|y|^2)  16 B, expanded-form filter scan
-//   double: (x,y,z,0)            32 B, direct-form scan
+//   float : [N,m_pad] filter records (-2y', |y'|^2) in the pair's translated frame (16 B), then [N,m_pad]
+//           original (x,y,z,0) records for the exact refine / fallback, then [N] centres
+//   double: [N,m_pad] (x,y,z,0), 32 B, direct-form scan
 template <typename T> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 constexpr int NN_CHUNK = 32;
 inline int nn_m_pad(int m) { return (m + NN_CHUNK - 1) / NN_CHUNK * NN_CHUNK; }
-inline size_t nn_packed_bytes(int N, int m, int elem_size) { return align_up((size_t)N * nn_m_pad(m) * 4 * elem_size); }
+inline size_t nn_packed_bytes(int N, int m, int elem_size) {
+  return elem_size == 4 ? align_up(((size_t)N * nn_m_pad(m) * 2 + (size_t)N) * 16) : align_up((size_t)N * nn_m_pad(m) * 32);
+}
 
 template <typename T>
 int nn_pack_targets(const T* tgt, int N, int m, int S, const int32_t* m_valid, typename Vec4<T>::type* packed, cudaStream_t st);

@@ -7,19 +7,22 @@
 // with one broadcast LDS.128 and evaluates Q distances against it.  This is FP32 CUDA-core
 // work (a K=3 distance is not a contraction worth tensor cores).
 //
-// fp32 (nn_scan_f32_kernel): a filter-and-refine scan.  Records hold (-2y, |y|^2), so
-//   v_j = |y_j|^2 - 2 x.y_j = d_j^2 - |x|^2     costs three FFMAs (half the FMA-pipe work of the
+// fp32 (nn_scan_f32_kernel): a filter-and-refine scan in a per-pair translated frame (x' = x - c,
+// y' = y - c, c = centre of the targets' bounding box, so that magnitudes are those of the cloud and
+// not of its distance from the origin).  Records hold (-2y', |y'|^2), so
+//   v_j = |y'_j|^2 - 2 x'.y'_j = d_j^2 - |x'|^2     costs three FFMAs (half the FMA-pipe work of the
 // direct form (x-y)^2, and the record operands are served from the operand-reuse cache, which
 // is what actually limits FP32 issue on this part: one register read per bank per cycle).
 // v_j is not exact (cancellation), so it is only a filter: per chunk of NN_CHUNK records a
 // running minimum (FMNMX3, ALU pipe), per query the best chunk, its value and the best value
 // among all *other* chunks.  If that runner-up is further away than a rigorous rounding bound
 // (nn_filter_margin), the nearest neighbour must be inside the best chunk and is found there
-// with the exact direct-form distance; otherwise the query is appended to its pair's list, and
-// the listed queries are rescanned exactly by the direct-form kernel (nn_scan_kernel<float,.,true>,
-// same tiling, records converted back to y in shared memory).  Either way the result is the
+// with the exact direct-form distance on the ORIGINAL coordinates; otherwise the query is appended
+// to its pair's list, and the listed queries are rescanned exactly by the direct-form kernel
+// (nn_scan_kernel<float,.,true>, same tiling, original records).  Either way the result is the
 // direct-form fp32 argmin with torch.argmin's first-minimum tie-break.  On the benchmark clouds
-// (|x| up to 28 m) about 1 % of the queries take the fallback.
+// (extent +-20 m) about 0.3 % of the queries take the fallback, wherever the clouds sit (without the
+// translation a cloud 1 km from the origin sent every query to the fallback: 10x slower).
 // fp64 (nn_scan_kernel<double,.,false>): plain direct-form scan, used by the fp64 parity tests.
 //
 // The target range is split over blockIdx.z when that is needed to fill 148 SMs or to keep the
@@ -36,40 +39,114 @@ template <typename T> __device__ __forceinline__ T t_min(T a, T b);
 template <> __device__ __forceinline__ float t_min<float>(float a, float b) { return fminf(a, b); }
 template <> __device__ __forceinline__ double t_min<double>(double a, double b) { return fmin(a, b); }
 
-// fp32 record (-2x, -2y, -2z, fl(|y|^2)): v = |y|^2 - 2 x.y = d^2 - |x|^2 with three FFMAs
-__device__ __forceinline__ void make_record(float x, float y, float z, float4& v) {
-  v.x = -2.0f * x; v.y = -2.0f * y; v.z = -2.0f * z;
-  v.w = (float)((double)x * x + (double)y * y + (double)z * z);
-}
+// fp32 packed layout per call: [N, m_pad] filter records | [N, m_pad] original (x,y,z,0) records | [N] centres.
+// The filter works in a per-pair translated frame (centre c of the targets' bounding box): with
+// y' = fl(y - c) the record is (-2y', fl(|y'|^2)) and v = |y'|^2 - 2 x'.y' = |x' - y'|^2 - |x'|^2 costs three
+// FFMAs.  Translating keeps |x'| at the size of the cloud instead of its distance from the origin, which is
+// what the cancellation error of the expanded form scales with (a cloud 1 km away would otherwise send every
+// query to the exact fallback).  Refine and fallback use the original records, so the result is unaffected.
 __device__ __forceinline__ void make_record(double x, double y, double z, double4& v) { v.x = x; v.y = y; v.z = z; v.w = 0.0; }
 
 template <typename T>
-__global__ void nn_pack_kernel(const T* __restrict__ tgt, int m, int m_pad, int S, const int32_t* __restrict__ m_valid,
-                               typename Vec4<T>::type* __restrict__ packed) {
+__global__ void nn_center_kernel(const T* __restrict__ tgt, int m_all, int S, const int32_t* __restrict__ m_valid, float4* __restrict__ centers) {
+  __shared__ float smin[3][8], smax[3][8];
+  const int b = blockIdx.x;
+  const T* tb = tgt + (size_t)b * m_all * S;
+  const int m = m_valid != nullptr ? min(max(m_valid[b], 1), m_all) : m_all;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = (float)tb[(size_t)j * S + c];
+      lo[c] = fminf(lo[c], v);
+      hi[c] = fmaxf(hi[c], v);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_down_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_down_sync(0xffffffffu, hi[c], o));
+    }
+    if (lane == 0) { smin[c][warp] = lo[c]; smax[c][warp] = hi[c]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float cc[3];
+    for (int c = 0; c < 3; ++c) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { smin[c][0] = fminf(smin[c][0], smin[c][w]); smax[c][0] = fmaxf(smax[c][0], smax[c][w]); }
+      cc[c] = 0.5f * smin[c][0] + 0.5f * smax[c][0];
+      if (!(fabsf(cc[c]) < 1.0e30f)) cc[c] = 0.0f;          // NaN / inf coordinates: no translation
+    }
+    centers[b] = make_float4(cc[0], cc[1], cc[2], 0.0f);
+  }
+}
+
+__global__ void nn_pack_f32_kernel(const float* __restrict__ tgt, int m, int m_pad, int S, const int32_t* __restrict__ m_valid,
+                                   const float4* __restrict__ centers, float4* __restrict__ filt, float4* __restrict__ orig) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m_pad) return;
-  typename Vec4<T>::type v;
   const int mb = m_valid != nullptr ? min(max(m_valid[b], 1), m) : m;      // rows >= m_valid[b] are padding: never a neighbour
+  float4 f, o;
   if (j < mb) {
-    const T* row = tgt + ((size_t)b * m + j) * S;
+    const float* row = tgt + ((size_t)b * m + j) * S;
+    const float4 c = centers[b];
+    const float y0 = (float)((double)row[0] - (double)c.x), y1 = (float)((double)row[1] - (double)c.y),
+                y2 = (float)((double)row[2] - (double)c.z);
+    f = make_float4(-2.0f * y0, -2.0f * y1, -2.0f * y2, (float)((double)y0 * y0 + (double)y1 * y1 + (double)y2 * y2));
+    o = make_float4(row[0], row[1], row[2], 0.0f);
+  } else {
+    const float far = Sentinel<float>::far();
+    f = make_float4(-2.0f * far, -2.0f * far, -2.0f * far, 3.0f * far * far);
+    o = make_float4(far, far, far, 0.0f);
+  }
+  filt[(size_t)b * m_pad + j] = f;
+  orig[(size_t)b * m_pad + j] = o;
+}
+
+__global__ void nn_pack_f64_kernel(const double* __restrict__ tgt, int m, int m_pad, int S, const int32_t* __restrict__ m_valid,
+                                   double4* __restrict__ packed) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m_pad) return;
+  double4 v;
+  const int mb = m_valid != nullptr ? min(max(m_valid[b], 1), m) : m;
+  if (j < mb) {
+    const double* row = tgt + ((size_t)b * m + j) * S;
     make_record(row[0], row[1], row[2], v);
   } else {
-    make_record(Sentinel<T>::far(), Sentinel<T>::far(), Sentinel<T>::far(), v);
+    make_record(Sentinel<double>::far(), Sentinel<double>::far(), Sentinel<double>::far(), v);
   }
   packed[(size_t)b * m_pad + j] = v;
 }
 
-template <typename T>
-int nn_pack_targets(const T* tgt, int N, int m, int S, const int32_t* m_valid, typename Vec4<T>::type* packed, cudaStream_t st) {
+// views into the fp32 packed buffer
+__host__ __device__ inline const float4* nn_orig_records(const float4* packed, int N, int m_pad) { return packed + (size_t)N * m_pad; }
+__host__ __device__ inline const float4* nn_centers(const float4* packed, int N, int m_pad) { return packed + 2 * (size_t)N * m_pad; }
+
+template <>
+int nn_pack_targets<float>(const float* tgt, int N, int m, int S, const int32_t* m_valid, float4* packed, cudaStream_t st) {
   const int m_pad = nn_m_pad(m);
+  float4* orig = packed + (size_t)N * m_pad;
+  float4* centers = packed + 2 * (size_t)N * m_pad;
+  nn_center_kernel<float><<<N, 256, 0, st>>>(tgt, m, S, m_valid, centers);
+  DICP_LAUNCH_CHECK();
   dim3 grid((m_pad + 255) / 256, N);
-  nn_pack_kernel<T><<<grid, 256, 0, st>>>(tgt, m, m_pad, S, m_valid, packed);
+  nn_pack_f32_kernel<<<grid, 256, 0, st>>>(tgt, m, m_pad, S, m_valid, centers, packed, orig);
   DICP_LAUNCH_CHECK();
   return 0;
 }
-template int nn_pack_targets<float>(const float*, int, int, int, const int32_t*, float4*, cudaStream_t);
-template int nn_pack_targets<double>(const double*, int, int, int, const int32_t*, double4*, cudaStream_t);
+template <>
+int nn_pack_targets<double>(const double* tgt, int N, int m, int S, const int32_t* m_valid, double4* packed, cudaStream_t st) {
+  const int m_pad = nn_m_pad(m);
+  dim3 grid((m_pad + 255) / 256, N);
+  nn_pack_f64_kernel<<<grid, 256, 0, st>>>(tgt, m, m_pad, S, m_valid, packed);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -82,12 +159,9 @@ constexpr int NN_THREADS = 128;   // fp64 scan
 constexpr int NN_FB_THREADS = 32; // fp32 exact fallback: one warp per CTA, few queries per pair
 constexpr int NN_TILE = 512;      // records per shared-memory stage
 
-// in-place conversion of a landed fp32 filter record (-2y, |y|^2) to the direct-form record (y, .)
-__device__ __forceinline__ void to_direct_record(float4& v) { v.x *= -0.5f; v.y *= -0.5f; v.z *= -0.5f; }
-__device__ __forceinline__ void to_direct_record(double4&) {}
-
-// Exact direct-form scan.  LIST == false: every query of the pair (fp64 path).  LIST == true: only
-// the queries listed in qlist[b, 0 .. qcount[b]) (the fp32 filter's ambiguous queries), no split.
+// Exact direct-form scan over (x,y,z,.) records.  LIST == false: every query of the pair (fp64 path).
+// LIST == true: only the queries listed in qlist[b, 0 .. qcount[b]) (the fp32 filter's ambiguous queries;
+// `packed` is then the array of ORIGINAL fp32 records).
 template <typename T, int Q, bool LIST, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
@@ -163,10 +237,6 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
     if (t + 1 < t_end) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     const int start = t * NN_TILE;
-    if (LIST) {      // each thread rewrites the records it copied itself (visible to it after the wait)
-      const int cnt = min(NN_TILE, m_pad - start);
-      for (int u = tid; u < cnt; u += NN_THREADS) to_direct_record(tile[buf][u]);
-    }
     __syncthreads();
     const int nchunks = min(NN_TILE, m_pad - start) / NN_CHUNK;
     for (int c = 0; c < nchunks; ++c) {
@@ -197,8 +267,7 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
     if (t_begin < t_end) {
 #pragma unroll 4
       for (int j = 0; j < NN_CHUNK; ++j) {
-        V4 y = ch[j];
-        if (LIST) to_direct_record(y);
+        const V4 y = ch[j];
         const T d = dist2<T>(x[k][0], x[k][1], x[k][2], y.x, y.y, y.z);
         if (found < 0 && d == best[k]) found = bchunk[k] * NN_CHUNK + j;
       }
@@ -226,23 +295,21 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
-// direct-form squared distance against a packed record (y = -a/2 exactly)
-__device__ __forceinline__ float dist2_rec(float x0, float x1, float x2, const float4& a) {
-  return dist2<float>(x0, x1, x2, -0.5f * a.x, -0.5f * a.y, -0.5f * a.z);
-}
-
 constexpr int NNF_THREADS = 128;
 constexpr int NNF_TILE = 512;     // records per shared-memory stage (8 KB)
 
-// Filter margin of one query.  u = 2^-24.  The filter value of target y is
+// Filter margin of one query, in the translated frame (x = x', y = y' below).  u = 2^-24.
+// The filter value of target y is
 //   v = fl(x0*a0 + fl(x1*a1 + fl(x2*a2 + h))),  a = -2y exactly, h = fl(|y|^2) (rounded once from fp64),
 // so |v - (d^2 - |x|^2)| <= u (|y|^2 + |s1| + |s2| + |s3|) (1 + 4u) with the exact partial sums
 //   s1 = |y|^2 - 2 x2 y2,  s2 = s1 - 2 x1 y1,  s3 = s2 - 2 x0 y0.
 // Only targets within rho = 2 d_best of the query can beat the best one, and for those each |s_i|
 // differs from its value at y = x (|x|^2 - 2 x2^2, ... , -|x|^2) by at most (2|x| + 2(|x_2|+..)) rho + rho^2.
 // A target in another chunk can only be the true (direct-form fp32) nearest neighbour if its filter
-// value is within  E_other + E_best + 10 u d_best^2  of the best chunk's; the constants below are
-// inflated for the rounding of this bound itself.
+// value is within  E_other + E_best + 10 u d_best^2  of the best chunk's.  The translation itself rounds:
+// x' = fl(x - c) and y' = fl(y - c) are each off by at most u|x'|, u|y'|, which moves a squared distance of
+// a target within rho by at most 2 rho u (2|x'| + rho).  The constants below are inflated for the rounding
+// of this bound itself.
 __device__ __forceinline__ float nn_filter_margin(float x0, float x1, float x2, float v_best) {
   const float U = 5.9604645e-8f;                                   // 2^-24
   const float xx = x0 * x0 + x1 * x1 + x2 * x2;
@@ -252,7 +319,7 @@ __device__ __forceinline__ float nn_filter_margin(float x0, float x1, float x2, 
   const float s1 = fabsf(xx - 2.0f * x2 * x2);
   const float s2 = fabsf(xx - 2.0f * x2 * x2 - 2.0f * x1 * x1);
   const float E = U * ((xn + rho) * (xn + rho) + s1 + s2 + xx + 14.5f * xn * rho + 3.0f * rho * rho);
-  return 2.1f * E + 16.0f * U * d2;
+  return 2.1f * E + 16.0f * U * d2 + 4.2f * U * rho * (2.0f * xn + rho);
 }
 
 template <int Q>
@@ -270,31 +337,35 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
   const int split = blockIdx.z;
   const int N = gridDim.y;
   const float4* tg = packed + (size_t)b * m_pad;
+  const float4* tg_orig = nn_orig_records(packed, N, m_pad) + (size_t)b * m_pad;
+  const float4 ctr = nn_centers(packed, N, m_pad)[b];
 
-  float C[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, r[3] = {0, 0, 0};
-  if (state != nullptr) {
-    const double* rec = state + (size_t)b * ST_STRIDE;
+  // the query in the target frame (ICP.py:137).  The transform is re-read and the point recomputed
+  // identically for the exact refine, so that neither stays in registers during the scan.
+  auto query_point = [&](int i, float* xo) {
+    const float* p = q + ((size_t)b * n + i) * 3;
+    const float pv[3] = {p[0], p[1], p[2]};
+    if (state != nullptr) {
+      const double* rec = state + (size_t)b * ST_STRIDE;
+      float C[9], a[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) C[i] = (float)rec[ST_C + i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) r[i] = (float)rec[ST_R + i];
-  }
-  float x[Q][3], best[Q], second[Q];
+      for (int c = 0; c < 9; ++c) C[c] = (float)rec[ST_C + c];
+      rotate(C, pv, a);
+      xo[0] = a[0] + (float)rec[ST_R]; xo[1] = a[1] + (float)rec[ST_R + 1]; xo[2] = a[2] + (float)rec[ST_R + 2];
+    } else {
+      xo[0] = pv[0]; xo[1] = pv[1]; xo[2] = pv[2];
+    }
+  };
+  float x[Q][3], best[Q], second[Q];           // x: the query in the translated filter frame
   int bchunk[Q];
   const int q0 = blockIdx.x * (NNF_THREADS * Q) + tid;
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
     int i = q0 + k * NNF_THREADS;
     if (i >= n) i = n - 1;
-    const float* p = q + ((size_t)b * n + i) * 3;
-    float pv[3] = {p[0], p[1], p[2]};
-    if (state != nullptr) {
-      float a[3];
-      rotate(C, pv, a);                                               // ICP.py:137
-      x[k][0] = a[0] + r[0]; x[k][1] = a[1] + r[1]; x[k][2] = a[2] + r[2];
-    } else {
-      x[k][0] = pv[0]; x[k][1] = pv[1]; x[k][2] = pv[2];
-    }
+    float xo[3];
+    query_point(i, xo);
+    x[k][0] = xo[0] - ctr.x; x[k][1] = xo[1] - ctr.y; x[k][2] = xo[2] - ctr.z;
     best[k] = INF; second[k] = INF; bchunk[k] = 0;
   }
 
@@ -367,10 +438,13 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
         if (slot < (unsigned int)fb_cap) fb_list[(size_t)b * fb_cap + slot] = i;
         fb_key[o] = 0xffffffffffffffffull;
       }
-      const float4* ch = tg + (size_t)bchunk[k] * NN_CHUNK;
+      float xo[3];
+      query_point(i, xo);
+      const float4* ch = tg_orig + (size_t)bchunk[k] * NN_CHUNK;
 #pragma unroll 4
       for (int j = 0; j < NN_CHUNK; ++j) {
-        const float d = dist2_rec(x[k][0], x[k][1], x[k][2], ch[j]);
+        const float4 y = ch[j];
+        const float d = dist2<float>(xo[0], xo[1], xo[2], y.x, y.y, y.z);
         if (d < bd) { bd = d; found = bchunk[k] * NN_CHUNK + j; }
       }
     }
@@ -508,7 +582,7 @@ static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const f
   if (gx < 4) gx = 4;
   if (gx > gx_cap) gx = gx_cap;
   dim3 grid(gx, N, fs);
-  nn_scan_kernel<float, NN_FB_Q, true, NN_FB_THREADS><<<grid, NN_FB_THREADS, 0, st>>>(q, state, packed, n, m_pad, tps, idx_out, d2_out, nullptr, nullptr,
+  nn_scan_kernel<float, NN_FB_Q, true, NN_FB_THREADS><<<grid, NN_FB_THREADS, 0, st>>>(q, state, nn_orig_records(packed, N, m_pad), n, m_pad, tps, idx_out, d2_out, nullptr, nullptr,
                                                                                       w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
   DICP_LAUNCH_CHECK();
   dim3 ugrid(1, N);
@@ -554,7 +628,7 @@ static int nn_argmin_impl(const T* q, const T* tgt, int N, int n, int m, int S, 
   cudaStream_t st = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);
   typedef typename Vec4<T>::type V4;
-  V4* packed = ar.take<V4>((size_t)N * nn_m_pad(m));
+  V4* packed = (V4*)ar.take<char>(nn_packed_bytes(N, m, sizeof(T)));
   int rc = nn_pack_targets<T>(tgt, N, m, S, nullptr, packed, st);
   if (rc) return rc;
   return nn_search<T>(q, nullptr, packed, N, n, m, idx_out, d2_out, nullptr, (char*)ws + ar.off, ws_bytes - ar.off, st);

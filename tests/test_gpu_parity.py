@@ -192,9 +192,10 @@ def test_nn_random_clouds(shape, dtype):
 
 @pytest.mark.parametrize("offset,extent", [(1000.0, 20.0), (30000.0, 5.0), (0.0, 2000.0)])
 def test_nn_far_from_origin_uses_exact_fallback(offset, extent):
-    """Clouds far from the origin make the fp32 expanded-form filter ambiguous for many queries
-    (cancellation ~ eps * |x|^2); those must be resolved by the exact fallback scan, so the
-    indices still equal the fp64-exact argmin on tie-free queries."""
+    """Clouds far from the origin / very large clouds stress the fp32 expanded-form filter (cancellation
+    ~ eps * |x'|^2 in the pair's translated frame, plus the rounding of the translation itself); whatever
+    the filter cannot certify must be resolved by the exact fallback scan, so the indices still equal the
+    fp64-exact argmin on tie-free queries."""
     gen = torch.Generator().manual_seed(int(offset) + 5)
     N, n, m = 2, 3000, 5000
     y = (torch.rand((N, m, 3), generator=gen, dtype=torch.float64) * 2 - 1) * extent + offset
