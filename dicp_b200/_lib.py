@@ -59,8 +59,11 @@ for _s in ("f32", "f64"):
     _SIGNATURES["dicp_gumbel_nn_" + _s] = ([_P, _P, _I, _I, _I, _I, _U64, _D, _D, _P, _P, _P], _I)
     _SIGNATURES["dicp_gumbel_nn_bwd_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _U64, _D, _D, _P, _P, _P, _P], _I)
     _SIGNATURES["dicp_gumbel_noise_" + _s] = ([_I, _I, _I, _U64, _D, _P, _P], _I)
-    _SIGNATURES["dicp_gn_accumulate_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams),
-                                               _P, _P, _P, _Z, _P], _I)
+_SIGNATURES["dicp_gn_accumulate_f32"] = ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams), _P, _P, _P], _I)
+_SIGNATURES["dicp_gn_accumulate_f64"] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams), _P, _P, _P], _I)
+_SIGNATURES["dicp_gn_blocks_per_pair"] = ([_I], _I)
+_SIGNATURES["dicp_gn_rows_bytes"] = ([_I, _I, _I], _Z)
+_SIGNATURES["dicp_gn_pack_rows_f32"] = ([_P, _I, _I, _I, _I, _P, _P], _I)
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 

@@ -142,7 +142,7 @@ bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, co
     constexpr int U = sizeof(T) == 4 ? 4 : 2;
     for (int base = blockIdx.x * (BW_THREADS * U); base < n; base += gridDim.x * (BW_THREADS * U)) {
       int ii[U], jj[U];
-      T p[U][3], q[U][3], nr[U][3], w0[U];
+      T p[U][3], q[U][3], nr[U][3], w0[U], gs[U][3], gw[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = base + u * BW_THREADS + threadIdx.x;
@@ -151,6 +151,9 @@ bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, co
         jj[u] = idx_b[ic];
         p[u][0] = src_b[3 * ic]; p[u][1] = src_b[3 * ic + 1]; p[u][2] = src_b[3 * ic + 2];
         w0[u] = w_init != nullptr ? w_init[(size_t)b * n + ic] : T(1);
+        // the running gradients this pass adds to: read with the other loads, not after the arithmetic
+        gs[u][0] = gs_b[3 * ic]; gs[u][1] = gs_b[3 * ic + 1]; gs[u][2] = gs_b[3 * ic + 2];
+        gw[u] = grad_w != nullptr ? grad_w[(size_t)b * n + ic] : T(0);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -164,9 +167,9 @@ bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, co
         eval_point<T, PT2PL, FASTW>(C, r, p[u], q[u], nr[u], w0[u], P, s);
         T abar[3], ebar[3], nbar[3], w0bar;
         point_backward<T, PT2PL>(s, w0[u], lam, del, abar, ebar, nbar, w0bar);
-        if (grad_w != nullptr) grad_w[(size_t)b * n + i] += w0bar;
+        if (grad_w != nullptr) grad_w[(size_t)b * n + i] = gw[u] + w0bar;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) gs_b[3 * i + c] += C[c] * abar[0] + C[3 + c] * abar[1] + C[6 + c] * abar[2];   // C^T abar
+        for (int c = 0; c < 3; ++c) gs_b[3 * i + c] = gs[u][c] + (C[c] * abar[0] + C[3 + c] * abar[1] + C[6 + c] * abar[2]);   // C^T abar
         T* grow = gt_b + (size_t)jj[u] * S;
         if (PT2PL) {
           const T g6[6] = {-ebar[0], -ebar[1], -ebar[2], nbar[0], nbar[1], nbar[2]};

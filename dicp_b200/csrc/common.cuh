@@ -80,6 +80,28 @@ __device__ __forceinline__ void load_target_row(const T* __restrict__ row, int S
     else { nr[0] = nr[1] = nr[2] = T(0); }
   }
 }
+// gather of one row of the re-laid fp32 target table (gn_pack_rows): ONE load instruction per
+// correspondence -- 32-byte (x,y,z,nx,ny,nz,0,0) records through the 256-bit load of sm_100
+// (LDG.E.256) for point-to-plane, 16-byte (x,y,z,0) records for point-to-point.  A warp's gather is
+// fully divergent, so the L1 processes one wavefront per lane and load instruction: one
+// instruction instead of three is a third of the L1 time, and the aligned record is one 32-byte
+// sector where a 24-byte row straddles two of them half of the time.
+template <typename T, bool PT2PL>
+__device__ __forceinline__ void load_packed_row(const void* __restrict__ rows, size_t row, T* q, T* nr) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (PT2PL) {
+      const float* p = static_cast<const float*>(rows) + row * 8;
+      float pad0, pad1;
+      asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=f"(q[0]), "=f"(q[1]), "=f"(q[2]), "=f"(nr[0]), "=f"(nr[1]), "=f"(nr[2]), "=f"(pad0), "=f"(pad1)
+          : "l"(p));
+    } else {
+      const float4 v = __ldg(static_cast<const float4*>(rows) + row);
+      q[0] = v.x; q[1] = v.y; q[2] = v.z;
+      nr[0] = nr[1] = nr[2] = 0.f;
+    }
+  }   // fp64 has no table: callers gather from the caller's rows (load_target_row)
+}
 // scatter-add of one 6-column gradient row: fp32 uses the 8-byte vector reduction (red.global.add.v2.f32)
 __device__ __forceinline__ void atomic_add_row6(float* row, const float* v) {
   atomicAdd(reinterpret_cast<float2*>(row), make_float2(v[0], v[1]));
@@ -150,8 +172,15 @@ int grid_search(const T* q, const double* state, int N, int n, int m, const Grid
 // ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------
 int gn_blocks_per_pair(int n);
 int bw_blocks_per_pair(int n);
+// where the accumulate kernel finds (C, r, active) of pair b: state + b * stride + {c, r, active}
+// (active < 0: every pair is active).  The loop passes its saved-state records, the stage API a bare [N,12].
+struct StateView { const double* base; int stride, c, r, active; };
+inline StateView state_view_records(const double* rec) { return StateView{rec, ST_STRIDE, ST_C, ST_R, ST_ACTIVE}; }
+// fp32 gather table of the targets (see load_packed_row); 0 bytes / no-op for fp64
+size_t gn_rows_bytes(int N, int m, int elem_size);
+template <typename T> int gn_pack_rows(const T* target, int N, int m, int S, bool pt2pl, void* rows, cudaStream_t st);
 template <typename T>
-int gn_accumulate(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* state,
+int gn_accumulate(const T* source, const T* target, const void* rows, const T* w_init, const int32_t* idx, StateView state,
                   int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,
                   double* partials, const int* stop_flag, cudaStream_t st);
 
@@ -170,6 +199,7 @@ struct IcpWorkspace {
   double* bw_partials; // [N, nblk, BW_NRED]
   void* grid_ws;       // uniform-grid index of the targets (nn_mode == DICP_NN_GRID)
   size_t grid_ws_bytes;
+  void* rows;          // fp32: [N, m] aligned gather records of the targets (gn_pack_rows); unused for fp64
   size_t total;
 };
 IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size);

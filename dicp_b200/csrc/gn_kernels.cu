@@ -28,7 +28,10 @@ void set_error(const char* fmt, ...) {
 }
 
 constexpr int GN_THREADS = 128;
-constexpr int GN_PTS_PER_THREAD = 16;  // 4 passes of 4: amortises the 31-value block reduction
+#ifndef GN_PTS
+#define GN_PTS 16
+#endif
+constexpr int GN_PTS_PER_THREAD = GN_PTS;  // 8 pipelined passes of 2: amortises the 31-value block reduction
 
 int bw_blocks_per_pair(int n) {          // backward point pass: 8 correspondences per thread (2 passes of 4)
   int nb = (n + GN_THREADS * 8 - 1) / (GN_THREADS * 8);
@@ -67,31 +70,32 @@ __device__ __forceinline__ void block_reduce_store(const T* vals, double* out, d
 
 template <typename T> struct GnUnroll;
 #ifndef GN_U
-#define GN_U 4
+#define GN_U 2
 #endif
-template <> struct GnUnroll<float> { static constexpr int U = GN_U; };
-template <> struct GnUnroll<double> { static constexpr int U = 2; };
+template <> struct GnUnroll<float> { static constexpr int U = GN_U; };   // correspondences per thread and pipeline stage
+template <> struct GnUnroll<double> { static constexpr int U = 1; };
 
 #ifndef GN_MINB
-#define GN_MINB 1
+#define GN_MINB 4
 #endif
+
 template <typename T, bool PT2PL, int DIM, bool FASTW>
-__global__ void __launch_bounds__(GN_THREADS, GN_MINB)
-gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
-                const int32_t* __restrict__ idx, const double* __restrict__ state, int n, int m, int S,
+__global__ void __launch_bounds__(GN_THREADS, sizeof(T) == 4 ? GN_MINB : 1)
+gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, const void* __restrict__ rows,
+                const T* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, int S,
                 WeightParams P, T* __restrict__ weights_out, long long w_pair_stride,
                 double* __restrict__ partials, const int* __restrict__ stop_flag) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   __shared__ double red_smem[(GN_THREADS / 32) * RED_N];
   constexpr int U = GnUnroll<T>::U;
   const int b = blockIdx.y;
-  const double* rec = state + (size_t)b * ST_STRIDE;
+  const double* rec = state.base + (size_t)b * state.stride;
   T C[9], r[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) C[i] = (T)rec[ST_C + i];
+  for (int i = 0; i < 9; ++i) C[i] = (T)rec[state.c + i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) r[i] = (T)rec[ST_R + i];
-  const T active = (T)rec[ST_ACTIVE];
+  for (int i = 0; i < 3; ++i) r[i] = (T)rec[state.r + i];
+  const T active = state.active >= 0 ? (T)rec[state.active] : T(1);
 
   T acc[RED_N];
 #pragma unroll
@@ -99,55 +103,122 @@ gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, cons
 
   const T* src_b = source + (size_t)b * n * 3;
   const T* tgt_b = target + (size_t)b * m * S;
+  const size_t row_b = (size_t)b * m;
+  const bool packed = sizeof(T) == 4 && rows != nullptr;
   const int32_t* idx_b = idx + (size_t)b * n;
   constexpr int R = PT2PL ? 1 : 3;
   T* wout = weights_out != nullptr ? weights_out + (size_t)b * w_pair_stride : nullptr;
 
-  // U correspondences per thread and pass; all index / point / row loads of a pass are issued
-  // before any arithmetic so that U dependent gathers are in flight per thread (HBM latency bound)
-  for (int base = blockIdx.x * (GN_THREADS * U); base < n; base += gridDim.x * (GN_THREADS * U)) {
-    int ii[U], jj[U];
-    T p[U][3], q[U][3], nr[U][3], w0[U];
+  // Three-stage software pipeline in registers, U correspondences per thread and stage: while pass t
+  // is evaluated, the row gathers of pass t+1 and the index / point / weight loads of pass t+2 are in
+  // flight (the gather address depends on the index, so one stage cannot cover both latencies).
+  // Without it a warp alternates between waiting for HBM and computing, and with 16 warps per SM
+  // (the 31 accumulators cost the registers) nothing else fills the gaps.
+  struct StageA { int ii[U], jj[U]; T p[U][3], w0[U]; };
+  struct StageB { T q[U][3], nr[U][3]; };
+  auto load_a = [&](StageA& a, int base) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = base + u * GN_THREADS + threadIdx.x;
-      ii[u] = i < n ? i : -1;
+      a.ii[u] = i < n ? i : -1;
       const int ic = i < n ? i : n - 1;
-      jj[u] = idx_b[ic];
-      p[u][0] = src_b[3 * ic]; p[u][1] = src_b[3 * ic + 1]; p[u][2] = src_b[3 * ic + 2];
-      w0[u] = (w_init != nullptr ? w_init[(size_t)b * n + ic] : T(1)) * active;          // ICP.py:257
+      a.jj[u] = idx_b[ic];
+      a.p[u][0] = src_b[3 * ic]; a.p[u][1] = src_b[3 * ic + 1]; a.p[u][2] = src_b[3 * ic + 2];
+      a.w0[u] = (w_init != nullptr ? w_init[(size_t)b * n + ic] : T(1)) * active;          // ICP.py:257
     }
+  };
+  auto load_b = [&](StageB& g, const StageA& a) {
+    if (packed) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      load_target_row<T, PT2PL>(tgt_b + (size_t)jj[u] * S, S, q[u], nr[u]);
+      for (int u = 0; u < U; ++u) load_packed_row<T, PT2PL>(rows, row_b + a.jj[u], g.q[u], g.nr[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) load_target_row<T, PT2PL>(tgt_b + (size_t)a.jj[u] * S, S, g.q[u], g.nr[u]);
     }
+  };
+  // one pipeline step: loads of pass t+2 into `an2`, gathers of pass t+1 (an1 -> gn1), arithmetic of pass t (ac, gc)
+  auto step = [&](const StageA& ac, const StageB& gc, const StageA& an1, StageB& gn1, StageA& an2, int base, int stride) {
+    load_a(an2, base + 2 * stride);
+    load_b(gn1, an1);
     // branch-free over the U correspondences so that their long dependent chains (sqrt, tanh, div)
     // interleave; lanes past the end of the cloud evaluate a clamped copy and are masked out
     PointEval<T> s[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) eval_point<T, PT2PL, FASTW>(C, r, p[u], q[u], nr[u], w0[u], P, s[u]);
+    for (int u = 0; u < U; ++u) eval_point<T, PT2PL, FASTW>(C, r, ac.p[u], gc.q[u], gc.nr[u], ac.w0[u], P, s[u]);
     if (base + GN_THREADS * U <= n) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) accum_point<T, PT2PL, DIM>(acc, s[u], w0[u], (T)P.thresh);
+      for (int u = 0; u < U; ++u) accum_point<T, PT2PL, DIM>(acc, s[u], ac.w0[u], (T)P.thresh);
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (ii[u] >= 0) accum_point<T, PT2PL, DIM>(acc, s[u], w0[u], (T)P.thresh);
+        if (ac.ii[u] >= 0) accum_point<T, PT2PL, DIM>(acc, s[u], ac.w0[u], (T)P.thresh);
     }
     if (wout != nullptr) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (ii[u] < 0) continue;
+        if (ac.ii[u] < 0) continue;
 #pragma unroll
-        for (int k = 0; k < R; ++k) wout[(size_t)ii[u] * R + k] = s[u].w;                   // ICP.py:222, 164-165
+        for (int k = 0; k < R; ++k) wout[(size_t)ac.ii[u] * R + k] = s[u].w;                   // ICP.py:222, 164-165
       }
+    }
+  };
+  const int stride = gridDim.x * (GN_THREADS * U);
+  int base = blockIdx.x * (GN_THREADS * U);
+  if (base < n) {
+    // the three stage buffers rotate by name over a loop unrolled by three: a register-to-register
+    // rotation at the end of each pass would wait for the loads it has just issued
+    StageA a0, a1, a2;
+    StageB g0, g1, g2;
+    load_a(a0, base);
+    load_a(a1, base + stride);
+    load_b(g0, a0);
+    for (;;) {
+      step(a0, g0, a1, g1, a2, base, stride);
+      if ((base += stride) >= n) break;
+      step(a1, g1, a2, g2, a0, base, stride);
+      if ((base += stride) >= n) break;
+      step(a2, g2, a0, g0, a1, base, stride);
+      if ((base += stride) >= n) break;
     }
   }
   block_reduce_store<T, RED_N>(acc, partials + ((size_t)b * gridDim.x + blockIdx.x) * RED_N, red_smem);
 }
 
+// ---- fp32 gather table ------------------------------------------------------------------
+size_t gn_rows_bytes(int N, int m, int elem_size) { return elem_size == 4 ? (size_t)N * m * 32 : 0; }
+
+template <bool PT2PL>
+__global__ void __launch_bounds__(256)
+gn_pack_rows_kernel(const float* __restrict__ target, size_t total, int S, float4* __restrict__ rows) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float* t = target + i * S;
+    if (PT2PL) {
+      const float2 a = *reinterpret_cast<const float2*>(t), b = *reinterpret_cast<const float2*>(t + 2),
+                   c = *reinterpret_cast<const float2*>(t + 4);
+      rows[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+      rows[2 * i + 1] = make_float4(c.x, c.y, 0.f, 0.f);
+    } else {
+      rows[i] = make_float4(t[0], t[1], t[2], 0.f);
+    }
+  }
+}
+
 template <typename T>
-int gn_accumulate(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* state,
+int gn_pack_rows(const T* target, int N, int m, int S, bool pt2pl, void* rows, cudaStream_t st) {
+  if constexpr (sizeof(T) == 4) {
+    const size_t total = (size_t)N * m;
+    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    if (pt2pl) gn_pack_rows_kernel<true><<<grid, 256, 0, st>>>(target, total, S, (float4*)rows);
+    else gn_pack_rows_kernel<false><<<grid, 256, 0, st>>>(target, total, S, (float4*)rows);
+    DICP_LAUNCH_CHECK();
+  }
+  return 0;
+}
+template int gn_pack_rows<float>(const float*, int, int, int, bool, void*, cudaStream_t);
+template int gn_pack_rows<double>(const double*, int, int, int, bool, void*, cudaStream_t);
+
+template <typename T>
+int gn_accumulate(const T* source, const T* target, const void* rows, const T* w_init, const int32_t* idx, StateView state,
                   int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,
                   double* partials, const int* stop_flag, cudaStream_t st) {
   const WeightParams P = make_weight_params(p);
@@ -156,10 +227,10 @@ int gn_accumulate(const T* source, const T* target, const T* w_init, const int32
   const bool fast = weight_params_fast(P);
 #define DICP_GN_LAUNCH(PL, DM)                                                                                                          \
   do {                                                                                                                                  \
-    if (fast) gn_accum_kernel<T, PL, DM, true><<<grid, GN_THREADS, 0, st>>>(source, target, w_init, idx, state, n, m, S, P, weights_out, \
-                                                                            w_pair_stride, partials, stop_flag);                        \
-    else gn_accum_kernel<T, PL, DM, false><<<grid, GN_THREADS, 0, st>>>(source, target, w_init, idx, state, n, m, S, P, weights_out,     \
-                                                                        w_pair_stride, partials, stop_flag);                            \
+    if (fast) gn_accum_kernel<T, PL, DM, true><<<grid, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P,        \
+                                                                            weights_out, w_pair_stride, partials, stop_flag);           \
+    else gn_accum_kernel<T, PL, DM, false><<<grid, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P,            \
+                                                                        weights_out, w_pair_stride, partials, stop_flag);               \
   } while (0)
   if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
   else if (pl) DICP_GN_LAUNCH(true, 2);
@@ -169,9 +240,9 @@ int gn_accumulate(const T* source, const T* target, const T* w_init, const int32
   DICP_LAUNCH_CHECK();
   return 0;
 }
-template int gn_accumulate<float>(const float*, const float*, const float*, const int32_t*, const double*, int, int, int, int,
+template int gn_accumulate<float>(const float*, const float*, const void*, const float*, const int32_t*, StateView, int, int, int, int,
                                   const dicp_params*, float*, long long, double*, const int*, cudaStream_t);
-template int gn_accumulate<double>(const double*, const double*, const double*, const int32_t*, const double*, int, int, int, int,
+template int gn_accumulate<double>(const double*, const double*, const void*, const double*, const int32_t*, StateView, int, int, int, int,
                                    const dicp_params*, double*, long long, double*, const int*, cudaStream_t);
 
 // sum the CTA partial rows of pair b in a fixed order (thread v sums slot v)
@@ -302,6 +373,7 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
   w.bw_partials = ar.take<double>((size_t)N * bw_blocks_per_pair(n) * BW_NRED);
   w.grid_ws_bytes = grid_ws_layout(nullptr, 0, N, n, m, elem_size).total;
   w.grid_ws = ar.take<char>(w.grid_ws_bytes);
+  w.rows = ar.take<char>(gn_rows_bytes(N, m, elem_size) > 0 ? gn_rows_bytes(N, m, elem_size) : 1);
   w.total = ar.off;
   return w;
 }
@@ -360,6 +432,10 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
     if (rc) return rc;
   }
 
+  rc = gn_pack_rows<T>(target, N, m, S, pl, w.rows, st);
+  if (rc) return rc;
+  const void* rows = sizeof(T) == 4 ? w.rows : nullptr;
+
   Ctrl h;
   memset(&h, 0, sizeof(h));
   for (int k = 0; k < K; ++k) {
@@ -368,7 +444,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
     if (use_grid) rc = grid_search<T>(source, rec_k, N, n, m, gw, true, idx_k, nullptr, &w.ctrl->stop, st);
     else rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st);
     if (rc) return rc;
-    rc = gn_accumulate<T>(source, target, w_init, idx_k, rec_k, N, n, m, S, p,
+    rc = gn_accumulate<T>(source, target, rows, w_init, idx_k, state_view_records(rec_k), N, n, m, S, p,
                           weights != nullptr ? weights + (size_t)k * nw : nullptr, (long long)K * nw, w.partials, &w.ctrl->stop, st);
     if (rc) return rc;
     gn_update_kernel<T><<<N, 128, 0, st>>>(w.partials, nblk, rec_k, rec_k + rec_stride, k, p->dim, p->const_iter, p->tolerance,
@@ -394,47 +470,17 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   return 0;
 }
 
+// stage API: the loop's accumulate kernel in ONE launch on a bare [N,12] (C, r); the per-CTA partial
+// rows come back as they are (gn_update_kernel sums them in index order in the loop)
 template <typename T>
-static int gn_accumulate_api(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* C_r,
-                             int N, int n, int m, int S, const dicp_params* p, T* weights_out, double* red_out,
-                             void* ws, size_t ws_bytes, void* stream);
-
-// expands [N,12] (C,r) into saved-state records so the stage API can reuse the loop's kernel
-__global__ void expand_state_kernel(const double* __restrict__ C_r, int N, double* __restrict__ state) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= N) return;
-  double* rec = state + (size_t)b * ST_STRIDE;
-  for (int i = 0; i < ST_STRIDE; ++i) rec[i] = 0.0;
-  for (int i = 0; i < 12; ++i) rec[i] = C_r[(size_t)b * 12 + i];
-  rec[ST_ACTIVE] = 1.0;
-}
-__global__ void sum_partials_kernel(const double* __restrict__ partials, int nblk, double* __restrict__ red_out) {
-  __shared__ double red[RED_N];
-  sum_partials(partials, blockIdx.x, nblk, RED_N, red);
-  if (threadIdx.x < RED_N) red_out[(size_t)blockIdx.x * RED_N + threadIdx.x] = red[threadIdx.x];
-}
-
-template <typename T>
-static int gn_accumulate_api(const T* source, const T* target, const T* w_init, const int32_t* idx, const double* C_r,
-                             int N, int n, int m, int S, const dicp_params* p, T* weights_out, double* red_out,
-                             void* ws, size_t ws_bytes, void* stream) {
-  DICP_CHECK_ARG(source && target && idx && C_r && p && red_out, "null pointer");
+static int gn_accumulate_api(const T* source, const T* target, const void* rows, const T* w_init, const int32_t* idx, const double* C_r,
+                             int N, int n, int m, int S, const dicp_params* p, T* weights_out, double* partials_out, void* stream) {
+  DICP_CHECK_ARG(source && target && idx && C_r && p && partials_out, "null pointer");
   DICP_CHECK_ARG(N >= 1 && N <= 65535 && n >= 1 && m >= 1 && (S == 3 || S == 6), "bad sizes");
   DICP_CHECK_ARG(p->icp_type != DICP_PT2PL || S == 6, "pt2pl needs a 6-column target");
-  const int nblk = gn_blocks_per_pair(n);
-  Arena ar(ws, ws_bytes);
-  double* state = ar.take<double>((size_t)N * ST_STRIDE);
-  double* partials = ar.take<double>((size_t)N * nblk * RED_N);
-  if (ws == nullptr || state == nullptr || partials == nullptr) { set_error("dicp_gn_accumulate: workspace too small"); return DICP_ERR_WORKSPACE; }
-  cudaStream_t st = (cudaStream_t)stream;
-  expand_state_kernel<<<(N + 127) / 128, 128, 0, st>>>(C_r, N, state);
-  DICP_LAUNCH_CHECK();
   const long long nw = (long long)n * (p->icp_type == DICP_PT2PL ? 1 : 3);
-  int rc = gn_accumulate<T>(source, target, w_init, idx, state, N, n, m, S, p, weights_out, nw, partials, nullptr, st);
-  if (rc) return rc;
-  sum_partials_kernel<<<N, 32, 0, st>>>(partials, nblk, red_out);
-  DICP_LAUNCH_CHECK();
-  return 0;
+  return gn_accumulate<T>(source, target, sizeof(T) == 4 ? rows : nullptr, w_init, idx, StateView{C_r, 12, 0, 9, -1}, N, n, m, S, p,
+                          weights_out, nw, partials_out, nullptr, (cudaStream_t)stream);
 }
 
 }  // namespace dicp
@@ -461,14 +507,23 @@ int dicp_icp_forward_f64(const double* source, const double* target, const doubl
   return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                         converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
 }
-int dicp_gn_accumulate_f32(const float* source, const float* target, const float* w_init, const int32_t* idx, const double* C_r,
-                           int N, int n, int m, int S, const dicp_params* params, float* weights_out, double* red_out,
-                           void* ws, size_t ws_bytes, void* stream) {
-  return dicp::gn_accumulate_api<float>(source, target, w_init, idx, C_r, N, n, m, S, params, weights_out, red_out, ws, ws_bytes, stream);
+int dicp_gn_blocks_per_pair(int n) { return dicp::gn_blocks_per_pair(n); }
+size_t dicp_gn_rows_bytes(int N, int m, int elem_size) { return dicp::gn_rows_bytes(N, m, elem_size); }
+int dicp_gn_pack_rows_f32(const float* target, int N, int m, int S, int icp_type, void* rows, void* stream) {
+  if (!target || !rows || N < 1 || m < 1 || (S != 3 && S != 6) || (icp_type == DICP_PT2PL && S != 6)) {
+    dicp::set_error("dicp_gn_pack_rows: bad arguments");
+    return DICP_ERR_ARG;
+  }
+  return dicp::gn_pack_rows<float>(target, N, m, S, icp_type == DICP_PT2PL, rows, (cudaStream_t)stream);
+}
+int dicp_gn_accumulate_f32(const float* source, const float* target, const void* rows, const float* w_init, const int32_t* idx,
+                           const double* C_r, int N, int n, int m, int S, const dicp_params* params, float* weights_out,
+                           double* partials_out, void* stream) {
+  return dicp::gn_accumulate_api<float>(source, target, rows, w_init, idx, C_r, N, n, m, S, params, weights_out, partials_out, stream);
 }
 int dicp_gn_accumulate_f64(const double* source, const double* target, const double* w_init, const int32_t* idx, const double* C_r,
-                           int N, int n, int m, int S, const dicp_params* params, double* weights_out, double* red_out,
-                           void* ws, size_t ws_bytes, void* stream) {
-  return dicp::gn_accumulate_api<double>(source, target, w_init, idx, C_r, N, n, m, S, params, weights_out, red_out, ws, ws_bytes, stream);
+                           int N, int n, int m, int S, const dicp_params* params, double* weights_out, double* partials_out,
+                           void* stream) {
+  return dicp::gn_accumulate_api<double>(source, target, nullptr, w_init, idx, C_r, N, n, m, S, params, weights_out, partials_out, stream);
 }
 }

@@ -168,16 +168,25 @@ DICP_API int dicp_icp_backward_f64(const double* source, const double* target, c
                           double* grad_source, double* grad_target, double* grad_w, double* grad_T_init,
                           void* ws, size_t ws_bytes, void* stream);
 
-/* ---- single Gauss-Newton stages, exported for tests and profiling ----------------------
- * One iteration's accumulate (ICP.py:143-200) on given correspondences: red_out [N,32]
- * doubles = upper-triangular A (21 | 6), b (6 | 3) at 21.., cost at 27, sum(w) 28,
- * #(w>thresh) 29, #(w_init>thresh) 30.  C_r [N,12] = row-major C then r, in double.     */
-DICP_API int dicp_gn_accumulate_f32(const float* source, const float* target, const float* w_init, const int32_t* idx,
-                           const double* C_r, int N, int n, int m, int S, const dicp_params* params,
-                           float* weights_out, double* red_out, void* ws, size_t ws_bytes, void* stream);
+/* ---- single Gauss-Newton stage, exported for tests and profiling -------------------------
+ * One iteration's accumulate (ICP.py:143-200) on given correspondences, exactly the kernel
+ * launch of the loop.  partials_out [N, dicp_gn_blocks_per_pair(n), 32] doubles (31 used): one row per
+ * CTA, which the loop's update kernel sums in index order; after the sum: upper-triangular A
+ * (21 | 6) at 0, b (6 | 3) at 21, cost at 27, sum(w) 28, #(w>thresh) 29, #(w_init>thresh) 30.
+ * C_r [N,12] = row-major C then r, in double.
+ * rows (fp32 only, may be NULL): the targets re-laid by dicp_gn_pack_rows_f32 as one aligned
+ * record per row (32 B (x,y,z,nx,ny,nz,0,0) for pt2pl, 16 B (x,y,z,0) for pt2pt; N*m*32 bytes
+ * reserved = dicp_gn_rows_bytes) so that a correspondence is one 256-/128-bit load; the
+ * loop builds this table once per call.  NULL gathers from `target` directly.               */
+DICP_API int dicp_gn_blocks_per_pair(int n);
+DICP_API size_t dicp_gn_rows_bytes(int N, int m, int elem_size);
+DICP_API int dicp_gn_pack_rows_f32(const float* target, int N, int m, int S, int icp_type, void* rows, void* stream);
+DICP_API int dicp_gn_accumulate_f32(const float* source, const float* target, const void* rows, const float* w_init,
+                           const int32_t* idx, const double* C_r, int N, int n, int m, int S,
+                           const dicp_params* params, float* weights_out, double* partials_out, void* stream);
 DICP_API int dicp_gn_accumulate_f64(const double* source, const double* target, const double* w_init, const int32_t* idx,
                            const double* C_r, int N, int n, int m, int S, const dicp_params* params,
-                           double* weights_out, double* red_out, void* ws, size_t ws_bytes, void* stream);
+                           double* weights_out, double* partials_out, void* stream);
 
 /* ---- Kabsch / SVD point-to-point step: the per-point half of dICP/ICP.py:557-563 ----------
  * sums[b] = ( sum_i p_i (3), sum_i q_i (3), sum_i q_i p_i^T (9, row-major), pad ),  q_i = tgt[b, idx[b,i], :3]

@@ -323,13 +323,28 @@ def test_gn_accumulate_stage_vs_oracle():
         p = _functions.make_params("pt2pl", 3, True, "cauchy", 0.5, 2.0, 5.0, 1e-12, 1, True, 0.0)
         s_d, t_d = src.to(dt).cuda(), tgt.to(dt).cuda()
         C_r = torch.cat((torch.eye(3, dtype=torch.float64).reshape(1, 9).repeat(N, 1), torch.zeros((N, 3), dtype=torch.float64)), 1).cuda()
-        red = torch.empty((N, 32), dtype=torch.float64, device="cuda")
+        nblk = lib.dicp_gn_blocks_per_pair(n)
         wout = torch.empty((N, n), dtype=dt, device="cuda")
-        ws = torch.empty(lib.dicp_icp_workspace_bytes(N, n, m, s_d.element_size()) + (1 << 20), dtype=torch.uint8, device="cuda")
-        rc = getattr(lib, "dicp_gn_accumulate_" + _lib.suffix(dt))(
-            _lib.ptr(s_d), _lib.ptr(t_d), None, _lib.ptr(idx), _lib.ptr(C_r), N, n, m, 6, ctypes.byref(p), _lib.ptr(wout),
-            _lib.ptr(red), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(s_d.device))
-        _lib.check(rc, "gn_accumulate")
+        st = _lib.stream_ptr(s_d.device)
+        variants = [None]
+        if dt == torch.float32:                       # also through the aligned gather table of the loop
+            rows = torch.empty(lib.dicp_gn_rows_bytes(N, m, 4), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.dicp_gn_pack_rows_f32(_lib.ptr(t_d), N, m, 6, p.icp_type, _lib.ptr(rows), st), "gn_pack_rows")
+            variants.append(rows)
+        reds = []
+        for rows in variants:
+            part = torch.empty((N, nblk, 32), dtype=torch.float64, device="cuda")
+            if dt == torch.float32:
+                rc = lib.dicp_gn_accumulate_f32(_lib.ptr(s_d), _lib.ptr(t_d), _lib.ptr(rows) if rows is not None else None, None,
+                                                _lib.ptr(idx), _lib.ptr(C_r), N, n, m, 6, ctypes.byref(p), _lib.ptr(wout), _lib.ptr(part), st)
+            else:
+                rc = lib.dicp_gn_accumulate_f64(_lib.ptr(s_d), _lib.ptr(t_d), None, _lib.ptr(idx), _lib.ptr(C_r), N, n, m, 6,
+                                                ctypes.byref(p), _lib.ptr(wout), _lib.ptr(part), st)
+            _lib.check(rc, "gn_accumulate")
+            reds.append(part.sum(1))
+        if len(reds) == 2:
+            assert torch.equal(reds[0], reds[1])      # same arithmetic, only the load path differs
+        red = reds[-1]
         red = red.cpu()
         A = torch.zeros((N, 6, 6), dtype=torch.float64)
         iu = torch.triu_indices(6, 6)
