@@ -194,7 +194,7 @@ def roofline_nn(src, tgt, pk):
     return {"kernel": "nn_scan_f32_kernel<8> + exact fallback (one dicp_nn_scan_f32 call)", "bound": "fp32",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of nn_scan_f32_kernel<8> at these shapes (profiles/r01_ncu_full_top_kernels.md)
-            "traffic": 132.2e6 if (N, n, m) == (256, 16384, 16384) else None, "ms_per_launch": sec * 1e3,
+            "traffic": 201.7e6 if (N, n, m) == (256, 16384, 16384) else None, "ms_per_launch": sec * 1e3,
             "executed_tflops": executed, "frac_executed": executed / peak,
             "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],
             "flop_per_pair_eval": {"algorithmic": 8, "executed": 6}, "units_per_launch": evals}, idx
@@ -225,8 +225,8 @@ def roofline_gn(src, tgt, idx, pk):
     ach = nbytes / sec / 1e9
     return {"kernel": "gn_accum_kernel<float,pt2pl,3> (one dicp_gn_accumulate_f32 call = the loop's single launch)", "bound": "hbm",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            # dram bytes of gn_accum_kernel at 256 pairs from the same ncu capture: 184.6 MB read + 15.7 MB written
-            "traffic": 200.3e6 if (N, n, m) == (256, 16384, 16384) else None,
+            # dram bytes of gn_accum_kernel at 256 pairs from the ncu capture in profiles/: 201.5 MB read + 15.8 MB written
+            "traffic": 217.3e6 if (N, n, m) == (256, 16384, 16384) else None,
             "ms_per_launch": sec * 1e3, "peak_source": pk["source"], "bytes_per_correspondence": 48,
             "units_per_launch": float(N) * n, "pairs": N}
 
@@ -319,8 +319,9 @@ def run_ours(args):
     if rank == 0:
         roof, idx = roofline_nn(src_d.detach(), tgt_d.detach(), pk)
         roof_gn = roofline_gn(src_d.detach(), tgt_d.detach(), idx, pk)
-        # the same kernel at 4x the pairs (measure the HBM fraction where launch latency does not dominate)
-        big = 4
+        # the same kernel at C5-on-one-GPU size, 2048 pairs = 33.5 M correspondences (measure the
+        # HBM fraction where launch latency does not dominate)
+        big = 8
         roof_gn["at_%d_pairs" % (big * PAIRS_PER_GPU)] = {
             k: v for k, v in roofline_gn(src_d.detach().repeat(big, 1, 1), tgt_d.detach().repeat(big, 1, 1), idx.repeat(big, 1), pk).items()
             if k in ("achieved", "frac", "ms_per_launch", "units_per_launch")}
