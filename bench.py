@@ -183,7 +183,7 @@ def roofline_nn(src, tgt, pk):
     _lib.check(lib.dicp_nn_pack_f32(_lib.ptr(tgt), N, m, 6, _lib.ptr(packed), st), "pack")
 
     def launch():
-        _lib.check(lib.dicp_nn_scan_f32(_lib.ptr(src), _lib.ptr(packed), N, n, m, _lib.ptr(idx), None, _lib.ptr(ws), ws.numel(), st), "scan")
+        _lib.check(lib.dicp_nn_scan_f32(_lib.ptr(src), None, _lib.ptr(packed), N, n, m, _lib.ptr(idx), None, _lib.ptr(ws), ws.numel(), st), "scan")
 
     sec = time_kernel(launch, reps=5)
     evals = float(N) * n * m

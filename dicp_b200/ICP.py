@@ -137,7 +137,8 @@ class ICP:
         params = _functions.make_params(
             self.icp_type, dim, self.diff, loss_name, loss_metric, trim_dist,
             self.config['dICP']['parameters']['tanh_steepness'], self.tolerance, self.max_iterations,
-            self.const_iter, self.match_ratio_thresh, self.check_every, self.nn_search)
+            self.const_iter, self.match_ratio_thresh, self.check_every,
+            self.nn_search if isinstance(self.nn_search, str) else 'brute')
 
         if m_valid is not None and (len(m_valid) != N or min(m_valid) == target.shape[1]):
             m_valid = None                                   # nothing is padded
@@ -145,9 +146,14 @@ class ICP:
             m_valid = torch.tensor(m_valid, dtype=torch.int32, device=dev)
         # host buffers are staged through the GPU; from pinned memory the copies are asynchronous and
         # stream-ordered in front of the kernels
+        source_d, target_d = source.to(dev, non_blocking=True), target.to(dev, non_blocking=True)
+        # nn_search may also be a search provider (e.g. parallel.SplitTargetSearch: the targets of one huge
+        # pair split over the GPUs of a process group); it is bound to this call's clouds and then asked
+        # for the correspondences of every iteration
+        nn_hook = None if isinstance(self.nn_search, str) else self.nn_search.bind(source_d.detach(), target_d.detach(), m_valid)
         pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
-            source.to(dev, non_blocking=True), target.to(dev, non_blocking=True), T_init.to(dev, non_blocking=True),
-            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid)
+            source_d, target_d, T_init.to(dev, non_blocking=True),
+            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook)
 
         if self.verbose:
             print("ICP converged in {} iterations".format(deltas.shape[1]))

@@ -186,10 +186,14 @@ class ICPFunction(torch.autograd.Function):
     forward(source (N,n,3), target (N,m,S), T_init (N,4,4), w_init (N,n) | None, params)
       -> pc, T (differentiable) and deltas, weights, costs, converged, num_iters, match_ratio
          (detached / non-differentiable, ICP.py:220-229, 288-292).
-    m_valid (N,) int32 or None: real row count of every target cloud of a ragged batch."""
+    m_valid (N,) int32 or None: real row count of every target cloud of a ragged batch.
+    nn_hook: None, or a callable `nn_hook(k, state_k, idx_k)` that replaces the loop's own
+      correspondence search (include/dicp_b200.h: dicp_icp_forward_hooked_*): `state_k` is the
+      (N, 64) float64 record tensor of iteration k (pass it to `dicp_nn_scan_*`), `idx_k` the
+      (N, n) int32 tensor to fill, both views of this call's saved buffers, on the current stream."""
 
     @staticmethod
-    def forward(ctx, source, target, T_init, w_init, params, m_valid=None):
+    def forward(ctx, source, target, T_init, w_init, params, m_valid=None, nn_hook=None):
         require_cuda()
         lib = load_library()
         dev, dt = source.device, source.dtype
@@ -214,11 +218,26 @@ class ICPFunction(torch.autograd.Function):
         saved_state = torch.empty((K + 1, N, _lib.STATE_STRIDE), dtype=torch.float64, device=dev)
         ws = _workspace(lib.dicp_icp_workspace_bytes(N, n, m, source.element_size()), dev)
         iters = ctypes.c_int32(0)
-        with torch.cuda.device(dev):
-            rc = getattr(lib, "dicp_icp_forward_" + sfx)(
-                ptr(source), ptr(target), ptr(T_init), ptr(w_init), ptr(m_valid), N, n, m, S, ctypes.byref(params),
+        args = (ptr(source), ptr(target), ptr(T_init), ptr(w_init), ptr(m_valid), N, n, m, S, ctypes.byref(params),
                 ptr(pc), ptr(T), ptr(deltas), ptr(weights), ptr(costs), ptr(converged), ptr(num_iters), ptr(match_ratio),
                 ptr(saved_idx), ptr(saved_state), ctypes.byref(iters), ptr(ws), ws.numel(), stream_ptr(dev))
+        with torch.cuda.device(dev):
+            if nn_hook is None:
+                rc = getattr(lib, "dicp_icp_forward_" + sfx)(*args)
+            else:
+                failure = []
+
+                def _c_hook(_user, k, _state_ptr, _idx_ptr):      # the pointers are saved_state[k] / saved_idx[k]
+                    try:
+                        nn_hook(int(k), saved_state[k], saved_idx[k])
+                        return 0
+                    except BaseException as exc:                  # noqa: BLE001 - must not unwind through C
+                        failure.append(exc)
+                        return _lib.DICP_ERR_HOOK
+                c_hook = _lib.NN_HOOK(_c_hook)
+                rc = getattr(lib, "dicp_icp_forward_hooked_" + sfx)(*args, c_hook, None)
+                if failure:
+                    raise failure[0]
         check(rc, "dicp_icp_forward_" + sfx)
         k_run = int(iters.value)
         ctx.params = params
@@ -252,4 +271,4 @@ class ICPFunction(torch.autograd.Function):
                 ptr(saved_idx), ptr(saved_state), ptr(g_T), ptr(g_pc), ptr(g_src), ptr(g_tgt), ptr(g_w), ptr(g_T0),
                 ptr(ws), ws.numel(), stream_ptr(dev))
         check(rc, "dicp_icp_backward_" + sfx)
-        return g_src, g_tgt, g_T0, g_w, None, None
+        return g_src, g_tgt, g_T0, g_w, None, None, None

@@ -15,6 +15,7 @@ DICP_PT2PL, DICP_PT2PT = 0, 1
 LOSS_IDS = {None: 0, "huber": 1, "cauchy": 2}
 NN_MODES = {"brute": 0, "grid": 1}
 STATE_STRIDE = 64
+DICP_ERR_HOOK = -4          # a Python correspondence hook raised (dicp_icp_forward_hooked_*)
 
 
 class DicpParams(ctypes.Structure):
@@ -33,6 +34,9 @@ _lock = threading.Lock()
 _P, _I, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 _U64, _D = ctypes.c_ulonglong, ctypes.c_double
 
+# int hook(void* user, int iteration, const double* state_k, int32_t* idx_k)   (include/dicp_b200.h: dicp_nn_hook)
+NN_HOOK = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p)
+
 _SIGNATURES = {
     "dicp_version": ([], ctypes.c_int),
     "dicp_last_error": ([], ctypes.c_char_p),
@@ -46,12 +50,13 @@ for _s in ("f32", "f64"):
     _SIGNATURES["dicp_nn_argmin_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_nn_argmin_grid_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_nn_pack_" + _s] = ([_P, _I, _I, _I, _P, _P], _I)
-    _SIGNATURES["dicp_nn_scan_" + _s] = ([_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
+    _SIGNATURES["dicp_nn_scan_" + _s] = ([_P, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_gather_rows_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)
     _SIGNATURES["dicp_gather_rows_bwd_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)
     _SIGNATURES["dicp_icp_forward_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams),
                                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                              ctypes.POINTER(ctypes.c_int32), _P, _Z, _P], _I)
+    _SIGNATURES["dicp_icp_forward_hooked_" + _s] = (_SIGNATURES["dicp_icp_forward_" + _s][0] + [NN_HOOK, _P], _I)
     _SIGNATURES["dicp_icp_backward_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams), _I,
                                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_kabsch_sums_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P], _I)

@@ -382,7 +382,7 @@ template <typename T>
 static int icp_forward_impl(const T* source, const T* target, const T* T_init, const T* w_init, const int32_t* m_valid, int N, int n,
                             int m, int S, const dicp_params* p, T* pc, T* T_out, T* deltas, T* weights, T* costs, uint8_t* converged,
                             T* num_iters, T* match_ratio, int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
-                            void* ws, size_t ws_bytes, void* stream) {
+                            void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook = nullptr, void* hook_user = nullptr) {
   DICP_CHECK_ARG(source && target && T_init && p && pc && T_out && deltas && costs && converged && num_iters && match_ratio &&
                  saved_idx && saved_state && iters_run_host, "null pointer");
   DICP_CHECK_ARG(N >= 1 && N <= 65535 && n >= 1 && m >= 1, "need 1 <= N <= 65535, n >= 1, m >= 1");
@@ -392,7 +392,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   DICP_CHECK_ARG(S == 3 || S == 6, "target must have 3 or 6 columns");
   DICP_CHECK_ARG(p->loss_id >= 0 && p->loss_id <= 2, "invalid loss id");                 // loss.py:19
   DICP_CHECK_ARG(p->max_iterations >= 1, "max_iterations must be >= 1");
-  DICP_CHECK_ARG(p->nn_mode == DICP_NN_BRUTE || p->nn_mode == DICP_NN_GRID, "invalid nn_mode");
+  DICP_CHECK_ARG(hook != nullptr || p->nn_mode == DICP_NN_BRUTE || p->nn_mode == DICP_NN_GRID, "invalid nn_mode");
   if (ws == nullptr || ws_bytes < plan_workspace(nullptr, 0, N, n, m, sizeof(T)).total) {
     set_error("dicp_icp_forward: workspace too small");
     return DICP_ERR_WORKSPACE;
@@ -414,7 +414,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   // optional spatial index of the (static) targets; a cloud so clustered that one cell holds a
   // large share of it (e.g. the 1000 x max(source) padding rows of a ragged batch stretch the
   // bounding box) would make the ring search degenerate, so such calls keep the tiled scan
-  bool use_grid = p->nn_mode == DICP_NN_GRID;
+  bool use_grid = hook == nullptr && p->nn_mode == DICP_NN_GRID;
   GridWorkspace gw;
   if (use_grid) {
     gw = grid_ws_layout(w.grid_ws, w.grid_ws_bytes, N, n, m, sizeof(T));
@@ -427,7 +427,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
     DICP_CUDA(cudaStreamSynchronize(st));
     if (max_occ > 64 && max_occ > m / 64) use_grid = false;
   }
-  if (!use_grid) {
+  if (!use_grid && hook == nullptr) {
     rc = nn_pack_targets<T>(target, N, m, S, m_valid, (V4*)w.packed, st);
     if (rc) return rc;
   }
@@ -441,7 +441,10 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   for (int k = 0; k < K; ++k) {
     double* rec_k = saved_state + (size_t)k * rec_stride;
     int32_t* idx_k = saved_idx + (size_t)k * N * n;
-    if (use_grid) rc = grid_search<T>(source, rec_k, N, n, m, gw, true, idx_k, nullptr, &w.ctrl->stop, st);
+    if (hook != nullptr) {
+      rc = hook(hook_user, k, rec_k, idx_k);     // the caller's search (e.g. targets split over GPUs), stream-ordered
+      if (rc) { set_error("dicp_icp_forward: the correspondence hook failed at iteration %d (code %d)", k, rc); return rc; }
+    } else if (use_grid) rc = grid_search<T>(source, rec_k, N, n, m, gw, true, idx_k, nullptr, &w.ctrl->stop, st);
     else rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st);
     if (rc) return rc;
     rc = gn_accumulate<T>(source, target, rows, w_init, idx_k, state_view_records(rec_k), N, n, m, S, p,
@@ -506,6 +509,24 @@ int dicp_icp_forward_f64(const double* source, const double* target, const doubl
                          double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream) {
   return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                         converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
+}
+int dicp_icp_forward_hooked_f32(const float* source, const float* target, const float* T_init, const float* w_init, const int32_t* m_valid,
+                                int N, int n, int m, int S, const dicp_params* params, float* pc, float* T_out, float* deltas, float* weights,
+                                float* costs, uint8_t* converged, float* num_iters, float* match_ratio, int32_t* saved_idx,
+                                double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook,
+                                void* user) {
+  if (hook == nullptr) { dicp::set_error("dicp_icp_forward_hooked: null hook"); return DICP_ERR_ARG; }
+  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+                                       converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream, hook, user);
+}
+int dicp_icp_forward_hooked_f64(const double* source, const double* target, const double* T_init, const double* w_init, const int32_t* m_valid,
+                                int N, int n, int m, int S, const dicp_params* params, double* pc, double* T_out, double* deltas, double* weights,
+                                double* costs, uint8_t* converged, double* num_iters, double* match_ratio, int32_t* saved_idx,
+                                double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook,
+                                void* user) {
+  if (hook == nullptr) { dicp::set_error("dicp_icp_forward_hooked: null hook"); return DICP_ERR_ARG; }
+  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+                                        converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream, hook, user);
 }
 int dicp_gn_blocks_per_pair(int n) { return dicp::gn_blocks_per_pair(n); }
 size_t dicp_gn_rows_bytes(int N, int m, int elem_size) { return dicp::gn_rows_bytes(N, m, elem_size); }

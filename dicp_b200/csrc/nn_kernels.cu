@@ -684,15 +684,15 @@ int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void*
   DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
   return dicp::nn_pack_targets<double>(tgt, N, m, S, nullptr, (double4*)packed, (cudaStream_t)stream);
 }
-int dicp_nn_scan_f32(const float* q, const void* packed, int N, int n, int m, int32_t* idx_out, float* d2_out, void* ws,
-                     size_t ws_bytes, void* stream) {
+int dicp_nn_scan_f32(const float* q, const double* state, const void* packed, int N, int n, int m, int32_t* idx_out, float* d2_out,
+                     void* ws, size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(q && packed && idx_out && N >= 1 && n >= 1 && m >= 1, "bad arguments");
-  return dicp::nn_search<float>(q, nullptr, (const float4*)packed, N, n, m, idx_out, d2_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+  return dicp::nn_search<float>(q, state, (const float4*)packed, N, n, m, idx_out, d2_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
-int dicp_nn_scan_f64(const double* q, const void* packed, int N, int n, int m, int32_t* idx_out, double* d2_out, void* ws,
-                     size_t ws_bytes, void* stream) {
+int dicp_nn_scan_f64(const double* q, const double* state, const void* packed, int N, int n, int m, int32_t* idx_out, double* d2_out,
+                     void* ws, size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(q && packed && idx_out && N >= 1 && n >= 1 && m >= 1, "bad arguments");
-  return dicp::nn_search<double>(q, nullptr, (const double4*)packed, N, n, m, idx_out, d2_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+  return dicp::nn_search<double>(q, state, (const double4*)packed, N, n, m, idx_out, d2_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 int dicp_gather_rows_f32(const float* tgt, const int32_t* idx, int N, int n, int m, int S, float* out, void* stream) {
   return dicp::gather_impl<float>(tgt, idx, N, n, m, S, out, stream, false);

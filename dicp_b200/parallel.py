@@ -2,7 +2,12 @@
 
 Cloud pairs are independent, so the hot path shards the batch dimension contiguously over the
 ranks and needs no collective.  Learning mode adds exactly one all-reduce per
-step over `[loss ‖ flattened parameter gradients]`."""
+step over `[loss ‖ flattened parameter gradients]`.
+
+A single huge pair does not shard over pairs; `SplitTargetSearch` splits its TARGETS instead
+(SURVEY.md §8 f-3): every rank scans its slice of the target cloud for all queries and one
+MIN all-reduce per iteration over packed (distance, index) keys merges the slices — the one
+place on the path with a real exchange step."""
 from typing import Iterable, List, Sequence, Tuple
 
 import torch
@@ -53,3 +58,99 @@ def gather_results(local: torch.Tensor, n_pairs: int, group=None) -> torch.Tenso
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat([o[: b - a] for o, (a, b) in zip(out, sizes)], dim=0)
+
+
+# ---------------------------------------------------------------------------------------
+# one pair, targets split over the ranks
+# ---------------------------------------------------------------------------------------
+_IDX_MASK = (1 << 32) - 1
+
+
+def pack_keys(d2: torch.Tensor, idx: torch.Tensor, offset: int) -> torch.Tensor:
+    """(squared distance, global index) as ONE int64 whose integer order is the lexicographic
+    order of the pair: the IEEE bit pattern of a non-negative fp32 is monotonic in its value, so
+    MIN over the keys of all slices is the nearest neighbour with `torch.argmin`'s first-minimum
+    tie-break (nn.py:35-36).  d2 float32 >= 0, idx int32 local to the slice that starts at `offset`."""
+    assert d2.dtype == torch.float32
+    hi = d2.contiguous().view(torch.int32).to(torch.int64) << 32
+    return hi | (idx.to(torch.int64) + int(offset))
+
+
+def unpack_keys(keys: torch.Tensor):
+    """-> (idx int32, d2 float32) of pack_keys."""
+    idx = (keys & _IDX_MASK).to(torch.int32)
+    d2 = (keys >> 32).to(torch.int32).view(torch.float32)
+    return idx, d2
+
+
+def reduce_min(t: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return t
+
+
+def merge_slices(d2: torch.Tensor, idx: torch.Tensor, offset: int, group=None) -> torch.Tensor:
+    """Global nearest-neighbour indices from every rank's slice result.  fp32: one MIN all-reduce
+    over packed keys; fp64 (96 bits do not fit a key): MIN over the distances, then MIN over the
+    indices of the ranks that hold that distance."""
+    if d2.dtype == torch.float32:
+        return unpack_keys(reduce_min(pack_keys(d2, idx, offset), group))[0]
+    best = reduce_min(d2.clone(), group)
+    cand = torch.where(d2 == best, idx.to(torch.int64) + int(offset), torch.full_like(idx, 2 ** 31 - 1, dtype=torch.int64))
+    return reduce_min(cand, group).to(torch.int32)
+
+
+class SplitTargetSearch:
+    """Correspondence search of `ICP.icp` with the target cloud split over the ranks of `group`.
+
+        icp = ICP(...); icp.nn_search = SplitTargetSearch()        # every rank, same inputs
+        res = icp.icp(source, target, T_init, ...)                 # identical results on every rank
+
+    Every rank holds the whole pair (a 130k-point cloud is 3 MB) and runs the cheap per-point
+    kernels redundantly; only the O(n m) scan is divided: rank r scans target rows
+    [lo_r, hi_r) with the same tiled brute-force kernels (`dicp_nn_pack_*` once per call,
+    `dicp_nn_scan_*` per iteration with the loop's own query transform), then `merge_slices`.
+    The scan's distance is the exact direct-form fp32/fp64 value whatever the slice, so the
+    merged indices — and with them T, pc and the gradients — are bit-identical to the
+    single-GPU brute-force call.  Ragged batches (m_valid) are not supported here."""
+
+    def __init__(self, group=None, rank: int = None, world_size: int = None):
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = rank if rank is not None else (dist.get_rank(group) if on else 0)
+        self.world_size = world_size if world_size is not None else (dist.get_world_size(group) if on else 1)
+
+    def bind(self, source: torch.Tensor, target: torch.Tensor, m_valid=None):
+        from . import _lib
+        from ._functions import _workspace
+        if m_valid is not None:
+            raise ValueError("SplitTargetSearch does not take ragged (padded) target batches")
+        lib = _lib.load_library()
+        N, n, _ = source.shape
+        m = target.shape[1]
+        lo, hi = shard_range(m, self.rank, self.world_size)
+        if hi <= lo:
+            raise ValueError("fewer target points (%d) than ranks (%d)" % (m, self.world_size))
+        dev, dt = source.device, source.dtype
+        sfx = _lib.suffix(dt)
+        st = _lib.stream_ptr(dev)
+        part = target[:, lo:hi, :3].contiguous()
+        ml = hi - lo
+        packed = torch.empty(lib.dicp_nn_packed_bytes(N, ml, source.element_size()), dtype=torch.uint8, device=dev)
+        _lib.check(getattr(lib, "dicp_nn_pack_" + sfx)(_lib.ptr(part), N, ml, 3, _lib.ptr(packed), st), "dicp_nn_pack")
+        ws = _workspace(lib.dicp_nn_workspace_bytes(N, n, ml, source.element_size()), dev)
+        idx_l = torch.empty((N, n), dtype=torch.int32, device=dev)
+        d2_l = torch.empty((N, n), dtype=dt, device=dev)
+        scan = getattr(lib, "dicp_nn_scan_" + sfx)
+
+        def local(state_k):
+            """this rank's slice: (squared distance, slice-local index, slice offset) of every query"""
+            _lib.check(scan(_lib.ptr(source), _lib.ptr(state_k), _lib.ptr(packed), N, n, ml, _lib.ptr(idx_l), _lib.ptr(d2_l),
+                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "dicp_nn_scan")
+            return d2_l, idx_l, lo
+
+        def hook(k, state_k, idx_k):
+            idx_k.copy_(merge_slices(*local(state_k), self.group))
+        hook.local = local
+        hook.keepalive = (part, packed, ws)
+        return hook

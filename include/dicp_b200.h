@@ -37,6 +37,7 @@ extern "C" {
 
 #define DICP_ERR_ARG       -1   /* bad size / null pointer / unsupported option */
 #define DICP_ERR_WORKSPACE -2   /* workspace too small */
+#define DICP_ERR_HOOK      -4   /* conventional return value of a failing dicp_nn_hook */
 #define DICP_ERR_SINGULAR  -3   /* a normal-equation matrix was exactly singular
                                    (the reference's torch.linalg.inv raises, ICP.py:201) */
 
@@ -104,14 +105,18 @@ DICP_API int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, 
 /* The two stages of dicp_nn_argmin_*, exported for profiling and for callers that search the
  * same targets repeatedly (the solver loop packs once per call): pack the targets into
  * records padded with sentinels to a multiple of 32 rows (`dicp_nn_packed_bytes` bytes; fp32:
- * 16-byte (-2x,-2y,-2z,|y|^2), fp64: 32-byte (x,y,z,0)), then scan.  `ws` for the scan is sized
- * by dicp_nn_workspace_bytes.                                                              */
+ * 16-byte filter records (-2y', |y'|^2) in the pair's translated frame y' = y - c, then the
+ * 16-byte original (x,y,z,0) records, then the centres c; fp64: 32-byte (x,y,z,0)), then scan.
+ * `state` (may be NULL): device records [N,DICP_STATE_STRIDE] doubles whose (C,r) transform the
+ * queries first, x = C q + r, with the arithmetic of the solver loop (ICP.py:137).  d2_out (may
+ * be NULL) receives the direct-form squared distance of the returned neighbour.  `ws` for the
+ * scan is sized by dicp_nn_workspace_bytes.                                                  */
 DICP_API size_t dicp_nn_packed_bytes(int N, int m, int elem_size);
 DICP_API int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream);
 DICP_API int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void* stream);
-DICP_API int dicp_nn_scan_f32(const float* q, const void* packed, int N, int n, int m,
+DICP_API int dicp_nn_scan_f32(const float* q, const double* state, const void* packed, int N, int n, int m,
                      int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
-DICP_API int dicp_nn_scan_f64(const double* q, const void* packed, int N, int n, int m,
+DICP_API int dicp_nn_scan_f64(const double* q, const double* state, const void* packed, int N, int n, int m,
                      int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- neighbour gather and its adjoint: replaces repeat+gather at dICP/nn.py:37-38 ------
@@ -150,6 +155,28 @@ DICP_API int dicp_icp_forward_f64(const double* source, const double* target, co
                          uint8_t* converged, double* num_iters, double* match_ratio,
                          int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
                          void* ws, size_t ws_bytes, void* stream);
+
+/* The same loop with the correspondence search supplied by the caller (second half:
+ * one huge pair whose TARGETS are split over several GPUs).  Every iteration k the loop calls
+ *     hook(user, k, state_k, idx_k)
+ * on the host, in stream order: state_k is the device record [N,DICP_STATE_STRIDE] whose (C,r)
+ * transform the source (pass it to dicp_nn_scan_*), idx_k the device [N,n] int32 the hook must
+ * fill (by work enqueued on `stream`) before the accumulate kernel that follows reads it.  A
+ * non-zero return aborts the call with that code.  params->nn_mode is ignored, nothing is
+ * packed; everything else is identical to dicp_icp_forward_*.                              */
+typedef int (*dicp_nn_hook)(void* user, int iteration, const double* state_k, int32_t* idx_k);
+DICP_API int dicp_icp_forward_hooked_f32(const float* source, const float* target, const float* T_init, const float* w_init,
+                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
+                         float* pc, float* T_out, float* deltas, float* weights, float* costs,
+                         uint8_t* converged, float* num_iters, float* match_ratio,
+                         int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
+                         void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook, void* user);
+DICP_API int dicp_icp_forward_hooked_f64(const double* source, const double* target, const double* T_init, const double* w_init,
+                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
+                         double* pc, double* T_out, double* deltas, double* weights, double* costs,
+                         uint8_t* converged, double* num_iters, double* match_ratio,
+                         int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
+                         void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook, void* user);
 
 /* ---- reverse pass: replaces torch autograd through ICP.py:132-280 -----
  * grad_T [N,4,4], grad_pc [N,n,3] (either may be NULL == zero)

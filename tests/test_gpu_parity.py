@@ -535,6 +535,74 @@ def test_icp_grid_mode_equals_brute_mode():
     _check(res, g, 1e-9)
 
 
+class _EmulatedSplit:
+    """W ranks of parallel.SplitTargetSearch in one process: every slice is scanned in turn and the
+    MIN all-reduce over the packed keys becomes an elementwise minimum."""
+
+    def __init__(self, world):
+        self.world = world
+
+    def bind(self, source, target, m_valid=None):
+        from dicp_b200.parallel import SplitTargetSearch, pack_keys, unpack_keys
+        hooks = [SplitTargetSearch(rank=r, world_size=self.world).bind(source, target, m_valid) for r in range(self.world)]
+
+        def hook(k, state_k, idx_k):
+            keys = None
+            for h in hooks:
+                d2, idx, lo = h.local(state_k)
+                kk = pack_keys(d2, idx, lo)
+                keys = kk if keys is None else torch.minimum(keys, kk)
+            idx_k.copy_(unpack_keys(keys)[0])
+        return hook
+
+
+def test_icp_with_split_targets_equals_single_gpu():
+    """SURVEY.md §8 f-3 (second half): one pair whose targets are split over ranks.  The hooked
+    loop (dicp_icp_forward_hooked_*) with the slice scans + key merge reproduces the plain
+    brute-force call bit for bit: T, weights, correspondences' effect on the gradients.  World
+    size 1 goes through the real provider, 3 ranks are emulated in-process (the collective itself
+    is covered by tests/test_parallel_gloo.py)."""
+    from oracle.dicp_oracle import make_wavy_pair
+    from dicp_b200.parallel import SplitTargetSearch
+    src, tgt = make_wavy_pair(2, 3000, 4001, seed=92, dtype=torch.float32)
+    T0 = torch.eye(4, device="cuda").repeat(2, 1, 1)
+    outs = {}
+    for name, search in (("brute", "brute"), ("one", SplitTargetSearch(rank=0, world_size=1)), ("three", _EmulatedSplit(3))):
+        icp = _icp("pt2pl", True, 6, 1e-12, const_iter=True)
+        icp.nn_search = search
+        s, t = src.cuda().requires_grad_(True), tgt.cuda().requires_grad_(True)
+        res = icp.icp(s, t, T0, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+        res["T"].sum().backward()
+        outs[name] = (res["T"].detach(), res["weights"], res["pc"].detach(), s.grad.clone())
+    for name in ("one", "three"):
+        for a, b in zip(outs["brute"], outs[name]):
+            assert torch.equal(a, b), name
+    # fp64 (two-step merge), pt2pt, tolerance-driven stop: same iteration count and transform
+    src64, tgt64 = make_wavy_pair(1, 1500, 1700, seed=93, dtype=torch.float64)
+    res = {}
+    for name, search in (("brute", "brute"), ("one", SplitTargetSearch(rank=0, world_size=1))):
+        icp = _icp("pt2pt", True, 30, 1e-9)
+        icp.nn_search = search
+        res[name] = icp.icp(src64.cuda(), tgt64[:, :, :3].contiguous().cuda(), torch.eye(4, dtype=torch.float64, device="cuda")[None],
+                            trim_dist=2.0, loss_fn={"name": "huber", "metric": 1.0}, dim=3)
+    assert torch.equal(res["brute"]["T"], res["one"]["T"]) and res["brute"]["deltas"].shape == res["one"]["deltas"].shape
+
+
+def test_search_hook_failure_surfaces_as_the_python_exception():
+    from oracle.dicp_oracle import make_wavy_pair
+
+    class Broken:
+        def bind(self, source, target, m_valid=None):
+            def hook(k, state_k, idx_k):
+                raise KeyError("no neighbours today")
+            return hook
+    src, tgt = make_wavy_pair(1, 256, 256, seed=94, dtype=torch.float32)
+    icp = _icp("pt2pl", True, 3, 1e-12, const_iter=True)
+    icp.nn_search = Broken()
+    with pytest.raises(KeyError):
+        icp.icp(src.cuda(), tgt.cuda(), torch.eye(4, device="cuda")[None], dim=3)
+
+
 def test_ragged_targets_use_valid_counts_not_pad_values():
     """the padding rows of a ragged target batch are excluded by count, so the
     result no longer depends on max(source) * target_pad_val being far away (it is not when

@@ -57,3 +57,64 @@ def test_allreduce_and_gather_world2():
             assert torch.allclose(g_theta, want_theta)
             assert torch.allclose(g_bias, torch.full((3,), 3.0, dtype=torch.float64))   # 1 + 2
             assert torch.equal(full, Tall)
+
+
+# ---------------------------------------------------------------------------------------
+# one pair with its targets split over the ranks: the merge of the slice results
+# ---------------------------------------------------------------------------------------
+def _split_case(dtype, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    N, n, m = 2, 300, 257                              # m not divisible by the world size
+    x = torch.randn((N, n, 3), generator=g, dtype=dtype)
+    y = torch.randn((N, m, 3), generator=g, dtype=dtype)
+    y[:, 200] = y[:, 17]                               # an exact duplicate: the tie must go to the lower index
+    x[:, 0] = y[:, 17]
+    return x, y
+
+
+def _direct_d2(x, y):
+    d = x[:, :, None, :] - y[:, None, :, :]
+    return (d * d).sum(-1)
+
+
+def test_pack_keys_order_and_roundtrip():
+    from dicp_b200.parallel import pack_keys, unpack_keys
+    d2 = torch.tensor([0.0, 1e-30, 1.0, 1.0, 3.5e38], dtype=torch.float32)
+    idx = torch.tensor([7, 0, 9, 3, 2 ** 31 - 1], dtype=torch.int32)
+    k = pack_keys(d2, idx, 0)
+    assert torch.equal(torch.argsort(k), torch.tensor([0, 1, 3, 2, 4]))     # by distance, then by index
+    i2, d2b = unpack_keys(k)
+    assert torch.equal(i2, idx) and torch.equal(d2b, d2)
+    assert torch.equal(unpack_keys(pack_keys(d2[:2], idx[:2], 1000))[0], idx[:2] + 1000)
+
+
+def _split_worker(rank, world, port, ret):
+    from dicp_b200.parallel import merge_slices
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = {}
+        for dtype in (torch.float32, torch.float64):
+            x, y = _split_case(dtype)
+            lo, hi = shard_range(y.shape[1], rank, world)
+            d2 = _direct_d2(x, y[:, lo:hi])                              # what the slice scan returns ...
+            best, idx = d2.min(-1)
+            out[str(dtype)] = merge_slices(best, idx.to(torch.int32), lo).clone()
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_target_merge_world2():
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_split_worker, args=(world, port, ret), nprocs=world, join=True)
+        for dtype in (torch.float32, torch.float64):
+            x, y = _split_case(dtype)
+            want = _direct_d2(x, y).argmin(-1).to(torch.int32)           # first minimum over the whole cloud
+            assert int(want[0, 0]) == 17
+            for r in range(world):
+                assert torch.equal(ret[r][str(dtype)], want)

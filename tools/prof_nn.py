@@ -25,7 +25,7 @@ _lib.check(lib.dicp_nn_pack_f32(_lib.ptr(tgt), N, n, 6, _lib.ptr(packed), st), "
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
 ev[0].record()
 for i in range(reps):
-    _lib.check(lib.dicp_nn_scan_f32(_lib.ptr(src), _lib.ptr(packed), N, n, n, _lib.ptr(idx), None, _lib.ptr(ws), ws.numel(), st), "scan")
+    _lib.check(lib.dicp_nn_scan_f32(_lib.ptr(src), None, _lib.ptr(packed), N, n, n, _lib.ptr(idx), None, _lib.ptr(ws), ws.numel(), st), "scan")
     ev[i + 1].record()
 torch.cuda.synchronize()
 ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
