@@ -12,9 +12,10 @@ process N x 256 pairs with no data-path collective (weak scaling; at N=8 this is
 in learning mode one NCCL all-reduce of [loss, d loss / d theta] closes every step.
 
 `value`  : pairs/s with inputs resident in HBM (timed with CUDA events on the launch stream).
-`e2e`    : pairs/s through the public API `dICP.ICP.ICP.icp` with pinned HOST buffers, the
-           host->device copies of the clouds and the device->host read of loss/T/grads inside
-           the timed region.
+`e2e`    : the same step (forward + backward) starting from pinned HOST buffers: the host->device
+           copies of the clouds and T_init, the call of the public API `dICP.ICP.ICP.icp`, the
+           backward to the input points and the device->host read of [loss, dloss/dtheta] and T
+           are all inside the timed region.
 `roofline`: the dominant kernel (nearest-neighbour scan, FP32 CUDA-core bound) timed alone
            with CUDA events; `roofline_gn`: the Gauss-Newton accumulate (HBM bound).
 `cpu_baseline`: the oracle port of the reference's torch-CPU path on a bounded sample.
@@ -269,18 +270,19 @@ def run_ours(args):
         loss.backward()
         return allreduce(torch.cat((loss.detach().reshape(1), theta.grad)))
 
-    theta_h = torch.arange(1, 13, dtype=torch.float32).requires_grad_(True)
-
     def step_e2e():
-        """public API with pinned HOST buffers: `icp.icp` stages the clouds through the GPU (H2D inside the call),
-        T comes back to the host, the loss and d loss / d theta are evaluated there (D2H of T, H2D of its gradient)."""
-        theta_h.grad = None
-        res = icp.icp(src_h, tgt_h, T0_h, trim_dist=TRIM, loss_fn=LOSS, dim=3)
-        assert res["T"].device.type == "cpu"
-        loss = learning_loss(res, theta_h)
+        """the same step from pinned HOST buffers: the clouds and T_init are copied to the GPU inside the step (H2D),
+        `icp.icp` runs forward, the backward reaches the input points as in step_resident, and the reduced
+        [loss, dloss/dtheta] and the transforms are read back to the host (D2H)."""
+        theta.grad = None
+        s = src_h.to(dev, non_blocking=True).requires_grad_(True)
+        t = tgt_h.to(dev, non_blocking=True).requires_grad_(True)
+        res = icp.icp(s, t, T0_h.to(dev, non_blocking=True), trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        loss = learning_loss(res, theta)
         loss.backward()
-        out = allreduce(torch.cat((loss.detach().reshape(1), theta_h.grad)).to(dev))
-        return out.cpu(), res["T"].detach()
+        assert s.grad is not None and t.grad is not None
+        out = allreduce(torch.cat((loss.detach().reshape(1), theta.grad)))
+        return out.cpu(), res["T"].detach().cpu()
 
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
@@ -326,26 +328,27 @@ def run_ours(args):
             k: v for k, v in roofline_gn(src_d.detach().repeat(big, 1, 1), tgt_d.detach().repeat(big, 1, 1), idx.repeat(big, 1), pk).items()
             if k in ("achieved", "frac", "ms_per_launch", "units_per_launch")}
         cpu = None
-        if True:    # rank 0 times the CPU baseline at every N (a bounded 2-pair sample, a few seconds)
+        if True:    # rank 0 times the CPU baseline at every N (a bounded sample: 8 x 1 pair, about 10 s)
             cores = os.cpu_count()
             torch.set_num_threads(cores)
             s1, t1 = src_h[:1].clone(), tgt_h[:1].clone()
             cpu_step(s1, t1)                        # warm-up (thread pool, allocator)
             t0 = time.perf_counter()
-            reps = 2
+            reps = 8                               # about 10 s of CPU work on the box's 16 cores
             for _ in range(reps):
                 cpu_step(s1, t1)
             cdt = time.perf_counter() - t0
             cpu = {"value": reps / cdt, "unit": "pairs/s", "cores": cores, "kind": "port",
                    "sample": "%d x 1 pair of the C3 workload (fwd+bwd, 10 it), oracle port of the reference torch-CPU path, "
                              "%d threads, %.1f s" % (reps, torch.get_num_threads(), cdt)}
-        # kernels of libdicp_b200.so per step: forward init + pack + 10 x (scan, merge, fallback, unpack, gn, update) + finalize,
-        # backward seed + 10 x (pair, points) + finish
-        launches_per_step = (2 + 6 * ITERS + 1) + (1 + 2 * ITERS + 1)
-        # per step: clouds + T_init up, the gradient of T up for the backward; T, the stats and the reduced
-        # [loss, dloss/dtheta] down (pc / weights / deltas / costs stay on the GPU until somebody reads them)
-        h2d = (src_h.numel() + tgt_h.numel() + T0_h.numel() + PAIRS_PER_GPU * 16 + 13) * 4
-        d2h = (PAIRS_PER_GPU * (16 + 3) + 13) * 4
+        # kernels of libdicp_b200.so per step (profiles/r01_launches.md): forward init, bbox centres, NN pack, gather
+        # records + 10 x (filter scan, exact fallback, unpack, GN accumulate, GN update) + finalize;
+        # backward seed + 10 x (pair, points) + final pair
+        launches_per_step = (4 + 5 * ITERS + 1) + (1 + 2 * ITERS + 1)
+        # per step: clouds + T_init up; T and the reduced [loss, dloss/dtheta] down (pc / weights / deltas / costs and
+        # the gradients of the clouds stay on the GPU, where a training loop would consume them)
+        h2d = (src_h.numel() + tgt_h.numel() + T0_h.numel()) * 4
+        d2h = (PAIRS_PER_GPU * 16 + 13) * 4
         line = {
             "metric": METRIC, "value": pairs_total * args.steps / sec, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -355,7 +358,7 @@ def run_ours(args):
                        "learning_mode_allreduce": "13 floats per step over NCCL" if world > 1 else "single GPU: no collective"},
             "clocks": clocks,
             "e2e": {"value": pairs_total * steps_e2e / sec_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * sec_e2e / steps_e2e, "api": "dICP.ICP.ICP.icp with pinned host tensors"},
+                    "ms_per_step": 1e3 * sec_e2e / steps_e2e, "api": "pinned host clouds -> H2D -> dICP.ICP.ICP.icp (forward) -> backward to the input points -> D2H of [loss, dloss/dtheta] and T"},
             "gpu_launches": launches_per_step * args.steps,
             "nn_search": "brute (tiled brute-force scan, the north-star kernel)",
             "alt_nn_grid": {"value": pairs_total * args.steps / sec_grid, "unit": "pairs/s", "ms_per_step": 1e3 * sec_grid / args.steps,
