@@ -296,7 +296,16 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
 __device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
 constexpr int NNF_THREADS = 128;
-constexpr int NNF_TILE = 512;     // records per shared-memory stage (8 KB)
+#ifndef NNF_TILE_RECORDS
+#define NNF_TILE_RECORDS 1024
+#endif
+#ifndef NNF_MINB
+#define NNF_MINB 4
+#endif
+#ifndef NNF_IL
+#define NNF_IL 4
+#endif
+constexpr int NNF_TILE = NNF_TILE_RECORDS;     // records per shared-memory stage (16 KB; two stages, 4 CTAs per SM)
 
 // Filter margin of one query, in the translated frame (x = x', y = y' below).  u = 2^-24.
 // The filter value of target y is
@@ -323,7 +332,7 @@ __device__ __forceinline__ float nn_filter_margin(float x0, float x1, float x2, 
 }
 
 template <int Q>
-__global__ void __launch_bounds__(NNF_THREADS, 4)
+__global__ void __launch_bounds__(NNF_THREADS, NNF_MINB)
 nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n,
                    int m_pad, int tiles_per_split, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
                    float* __restrict__ part_d2, int32_t* __restrict__ part_idx, unsigned int* __restrict__ fb_count,
@@ -394,25 +403,29 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
       for (int k = 0; k < Q; ++k) cm[k] = INF;
       const float4* ch = &tile[buf][c * NN_CHUNK];
 #pragma unroll
-      for (int j = 0; j < NN_CHUNK; j += 2) {
+      for (int j = 0; j < NN_CHUNK; j += NNF_IL) {
         // one broadcast LDS.128 per record; the record's components sit in the same operand slot of
         // Q consecutive FFMAs, so they are served from the operand-reuse cache, not the register file
-        const float4 a0 = ch[j], a1 = ch[j + 1];
-        float v0[Q], v1[Q];
+        float4 a[NNF_IL];
+        float v[NNF_IL][Q];
 #pragma unroll
-        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][2], a0.z, a0.w);
+        for (int i = 0; i < NNF_IL; ++i) a[i] = ch[j + i];
 #pragma unroll
-        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][2], a1.z, a1.w);
+        for (int i = 0; i < NNF_IL; ++i)
 #pragma unroll
-        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][1], a0.y, v0[k]);
+          for (int k = 0; k < Q; ++k) v[i][k] = __fmaf_rn(x[k][2], a[i].z, a[i].w);
 #pragma unroll
-        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][1], a1.y, v1[k]);
+        for (int i = 0; i < NNF_IL; ++i)
 #pragma unroll
-        for (int k = 0; k < Q; ++k) v0[k] = __fmaf_rn(x[k][0], a0.x, v0[k]);
+          for (int k = 0; k < Q; ++k) v[i][k] = __fmaf_rn(x[k][1], a[i].y, v[i][k]);
 #pragma unroll
-        for (int k = 0; k < Q; ++k) v1[k] = __fmaf_rn(x[k][0], a1.x, v1[k]);
+        for (int i = 0; i < NNF_IL; ++i)
 #pragma unroll
-        for (int k = 0; k < Q; ++k) cm[k] = min3(cm[k], v0[k], v1[k]);
+          for (int k = 0; k < Q; ++k) v[i][k] = __fmaf_rn(x[k][0], a[i].x, v[i][k]);
+#pragma unroll
+        for (int i = 0; i < NNF_IL; i += 2)
+#pragma unroll
+          for (int k = 0; k < Q; ++k) cm[k] = min3(cm[k], v[i][k], v[i + 1][k]);
       }
 #pragma unroll
       for (int k = 0; k < Q; ++k) {
