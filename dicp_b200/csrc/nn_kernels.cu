@@ -300,12 +300,12 @@ constexpr int NNF_THREADS = 128;
 #define NNF_TILE_RECORDS 1024
 #endif
 #ifndef NNF_MINB
-#define NNF_MINB 4
+#define NNF_MINB 5
 #endif
 #ifndef NNF_IL
 #define NNF_IL 4
 #endif
-constexpr int NNF_TILE = NNF_TILE_RECORDS;     // records per shared-memory stage (16 KB; two stages, 4 CTAs per SM)
+constexpr int NNF_TILE = NNF_TILE_RECORDS;     // records per shared-memory stage (16 KB; two stages, 5 CTAs per SM)
 
 // Filter margin of one query, in the translated frame (x = x', y = y' below).  u = 2^-24.
 // The filter value of target y is
@@ -512,7 +512,8 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
   const int m_pad = nn_m_pad(m);
   int ctas_per_sm;
   if (elem_size == 4) {
-    // 8 queries per thread, 128 registers, 4 CTAs / SM (tools/nn_tune.cu: 8.75 ms at C3; 16 queries / 2 CTAs: 8.80 ms)
+    // 8 queries per thread, 93 registers, 5 CTAs / SM (profiles/r01_nn_tuning.md).  The split heuristic below
+    // counts 4 per SM: at C3 (4096 CTAs) a fifth resident CTA must not tip the launch into two target splits
     p.threads = NNF_THREADS; p.tile = NNF_TILE; p.q = 8;
     ctas_per_sm = 4;
   } else {
