@@ -677,6 +677,42 @@ static int gather_impl(const T* tgt, const int32_t* idx, int N, int n, int m, in
   return 0;
 }
 
+// ---- one pair, targets split over GPUs: merge of the slice results over NVLink peer memory -----
+// Every rank folds the (distance, global index) key of each query into the key buffer of EVERY rank
+// with a 64-bit system-scope atomic MIN (red.min.u64 over NVLink); after a cross-GPU barrier each
+// buffer holds the global nearest neighbour.  The bit pattern of a non-negative fp32 is monotonic
+// in its value, so integer MIN == nearest neighbour with the first-minimum tie-break (nn.py:35-36).
+constexpr int NN_MAX_PEERS = 16;
+struct PeerKeys { unsigned long long* p[NN_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256)
+nn_push_keys_kernel(const float* __restrict__ d2, const int32_t* __restrict__ idx, int offset, size_t count, PeerKeys peers, int world,
+                    int first_peer, unsigned long long* __restrict__ reset_buf) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d2[i]) << 32) | (unsigned int)(idx[i] + offset);
+    for (int j = 0; j < world; ++j) {
+      int r = first_peer + j;                  // every rank starts at a different peer: spreads the traffic over the links
+      if (r >= world) r -= world;
+      atomicMin_system(peers.p[r] + i, key);
+    }
+    if (reset_buf != nullptr) reset_buf[i] = ~0ull;      // the buffer of the iteration after this one
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nn_unpack_keys_kernel(const unsigned long long* __restrict__ keys, size_t count, int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = keys[i];
+    idx_out[i] = (int32_t)(key & 0xffffffffull);
+    if (d2_out != nullptr) d2_out[i] = __uint_as_float((unsigned int)(key >> 32));
+  }
+}
+
+static int grid_for(size_t count) {
+  const size_t b = (count + 255) / 256;
+  return (int)(b < 148 * 8 ? (b > 0 ? b : 1) : 148 * 8);
+}
+
 }  // namespace dicp
 
 extern "C" {
@@ -707,6 +743,23 @@ int dicp_nn_scan_f64(const double* q, const double* state, const void* packed, i
                      void* ws, size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(q && packed && idx_out && N >= 1 && n >= 1 && m >= 1, "bad arguments");
   return dicp::nn_search<double>(q, state, (const double4*)packed, N, n, m, idx_out, d2_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+int dicp_nn_push_keys_f32(const float* d2, const int32_t* idx, int offset, size_t count, const uint64_t* peer_bufs, int world,
+                          int first_peer, void* reset_buf, void* stream) {
+  DICP_CHECK_ARG(d2 && idx && peer_bufs && count >= 1 && world >= 1 && world <= dicp::NN_MAX_PEERS && first_peer >= 0 && first_peer < world,
+                 "bad arguments");
+  dicp::PeerKeys pk;
+  for (int r = 0; r < dicp::NN_MAX_PEERS; ++r) pk.p[r] = r < world ? (unsigned long long*)(uintptr_t)peer_bufs[r] : nullptr;
+  dicp::nn_push_keys_kernel<<<dicp::grid_for(count), 256, 0, (cudaStream_t)stream>>>(d2, idx, offset, count, pk, world, first_peer,
+                                                                                     (unsigned long long*)reset_buf);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+int dicp_nn_unpack_keys_f32(const void* keys, size_t count, int32_t* idx_out, float* d2_out, void* stream) {
+  DICP_CHECK_ARG(keys && idx_out && count >= 1, "bad arguments");
+  dicp::nn_unpack_keys_kernel<<<dicp::grid_for(count), 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)keys, count, idx_out, d2_out);
+  DICP_LAUNCH_CHECK();
+  return 0;
 }
 int dicp_gather_rows_f32(const float* tgt, const int32_t* idx, int N, int n, int m, int S, float* out, void* stream) {
   return dicp::gather_impl<float>(tgt, idx, N, n, m, S, out, stream, false);

@@ -112,13 +112,43 @@ class SplitTargetSearch:
     `dicp_nn_scan_*` per iteration with the loop's own query transform), then `merge_slices`.
     The scan's distance is the exact direct-form fp32/fp64 value whatever the slice, so the
     merged indices — and with them T, pc and the gradients — are bit-identical to the
-    single-GPU brute-force call.  Ragged batches (m_valid) are not supported here."""
+    single-GPU brute-force call.  Ragged batches (m_valid) are not supported here.
 
-    def __init__(self, group=None, rank: int = None, world_size: int = None):
+    transport: how the slices are merged.
+      'nccl'  one MIN all-reduce per iteration (`merge_slices`);
+      'peer'  (fp32) no collective library on the path: a kernel of ours folds every rank's keys into
+              the key buffers of ALL ranks with 64-bit system-scope atomic MINs over NVLink peer memory
+              (`dicp_nn_push_keys_f32`; buffers from torch's symmetric-memory allocator), one
+              cross-GPU barrier, `dicp_nn_unpack_keys_f32`;
+      'auto'  'peer' when fp32, more than one rank and the peer buffers can be set up, else 'nccl'."""
+
+    def __init__(self, group=None, rank: int = None, world_size: int = None, transport: str = "auto"):
+        assert transport in ("auto", "nccl", "peer")
         self.group = group
+        self.transport = transport
+        self.used_transport = None            # what the last bind() chose
+        self._peer = {}                       # (count, device) -> (keys tensor, handle, per-buffer address arrays)
         on = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank(group) if on else 0)
         self.world_size = world_size if world_size is not None else (dist.get_world_size(group) if on else 1)
+
+    def _peer_buffers(self, count, dev):
+        """two key buffers of `count` u64 per rank, mapped into every rank (double-buffered over the
+        iterations: iteration k merges in buffer k & 1 and resets the other one)"""
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        key = (count, str(dev))
+        if key not in self._peer:
+            group = self.group if self.group is not None else dist.group.WORLD
+            keys = symm_mem.empty(2 * count, dtype=torch.int64, device=dev)
+            hdl = symm_mem.rendezvous(keys, group)
+            addr = [(ctypes.c_uint64 * self.world_size)(*[int(hdl.buffer_ptrs[r]) + j * count * 8 for r in range(self.world_size)])
+                    for j in (0, 1)]
+            self._peer[key] = (keys, hdl, addr)
+        keys, hdl, addr = self._peer[key]
+        keys.fill_(-1)                        # all ones = +inf key; nobody pushes before the barrier below
+        hdl.barrier(channel=0)
+        return keys, hdl, addr
 
     def bind(self, source: torch.Tensor, target: torch.Tensor, m_valid=None):
         from . import _lib
@@ -149,8 +179,34 @@ class SplitTargetSearch:
                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "dicp_nn_scan")
             return d2_l, idx_l, lo
 
-        def hook(k, state_k, idx_k):
-            idx_k.copy_(merge_slices(*local(state_k), self.group))
+        transport = self.transport
+        peer = None
+        if transport != "nccl" and dt == torch.float32 and self.world_size > 1 and dist.is_initialized():
+            try:
+                peer = self._peer_buffers(N * n, dev)
+            except Exception:                 # noqa: BLE001 - no peer access / allocator: the collective still works
+                if transport == "peer":
+                    raise
+        elif transport == "peer":
+            raise ValueError("transport='peer' needs fp32 clouds and an initialised process group with more than one rank")
+        self.used_transport = "peer" if peer is not None else "nccl"
+
+        if peer is None:
+            def hook(k, state_k, idx_k):
+                idx_k.copy_(merge_slices(*local(state_k), self.group))
+        else:
+            keys, hdl, addr = peer
+            count = N * n
+
+            def hook(k, state_k, idx_k):
+                d2, idx, off = local(state_k)
+                j = k & 1
+                stream = _lib.stream_ptr(dev)
+                _lib.check(lib.dicp_nn_push_keys_f32(_lib.ptr(d2), _lib.ptr(idx), off, count, addr[j], self.world_size, self.rank,
+                                                     _lib.ptr(keys[(1 - j) * count:]), stream), "dicp_nn_push_keys")
+                hdl.barrier(channel=0)        # every rank's keys have landed everywhere
+                _lib.check(lib.dicp_nn_unpack_keys_f32(_lib.ptr(keys[j * count:]), count, _lib.ptr(idx_k), None, stream),
+                           "dicp_nn_unpack_keys")
         hook.local = local
         hook.keepalive = (part, packed, ws)
         return hook

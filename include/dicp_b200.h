@@ -119,6 +119,17 @@ DICP_API int dicp_nn_scan_f32(const float* q, const double* state, const void* p
 DICP_API int dicp_nn_scan_f64(const double* q, const double* state, const void* packed, int N, int n, int m,
                      int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Merge of slice results when ONE pair's targets are split over GPUs, over
+ * NVLink peer memory instead of a collective library: every rank folds key = (bits(d2) << 32) |
+ * (idx + offset) of each query into the key buffer of every rank (peer_bufs: HOST array of
+ * `world` device addresses of count u64, peer-mapped, preset to all-ones) with a system-scope
+ * 64-bit atomic MIN, starting at peer `first_peer`; reset_buf (may be NULL) is a local buffer
+ * it also resets to all-ones for a later iteration.  After a cross-GPU barrier (the caller's),
+ * dicp_nn_unpack_keys_f32 turns a rank's own buffer into indices (and distances).             */
+DICP_API int dicp_nn_push_keys_f32(const float* d2, const int32_t* idx, int offset, size_t count,
+                          const uint64_t* peer_bufs, int world, int first_peer, void* reset_buf, void* stream);
+DICP_API int dicp_nn_unpack_keys_f32(const void* keys, size_t count, int32_t* idx_out, float* d2_out, void* stream);
+
 /* ---- neighbour gather and its adjoint: replaces repeat+gather at dICP/nn.py:37-38 ------
  * out[b,i,:] = tgt[b,idx[b,i],:]           grad_tgt[b,idx[b,i],:] += grad_out[b,i,:]
  * grad_tgt must be zero-initialised by the caller (it is accumulated into).             */

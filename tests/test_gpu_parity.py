@@ -588,6 +588,37 @@ def test_icp_with_split_targets_equals_single_gpu():
     assert torch.equal(res["brute"]["T"], res["one"]["T"]) and res["brute"]["deltas"].shape == res["one"]["deltas"].shape
 
 
+def test_peer_key_merge_kernels_on_one_device():
+    """dicp_nn_push_keys_f32 / dicp_nn_unpack_keys_f32 (the NVLink peer-memory merge of
+    SplitTargetSearch) with the "peers" being two buffers of this GPU: three slices folded into
+    both buffers give, in both, the minimum distance with the lowest global index on ties."""
+    import ctypes
+    from dicp_b200 import _lib
+    from dicp_b200.parallel import pack_keys, unpack_keys
+    lib = _lib.load_library()
+    g = torch.Generator().manual_seed(7)
+    count, W = 70001, 3
+    d2 = torch.rand((W, count), generator=g).mul_(4.0).round_().div_(4.0).cuda()       # many exact ties
+    idx = torch.randint(0, 1000, (W, count), generator=g, dtype=torch.int32).cuda()
+    offs = [0, 1000, 2000]
+    bufs = [torch.full((count,), -1, dtype=torch.int64, device="cuda") for _ in range(2)]
+    spare = torch.zeros((count,), dtype=torch.int64, device="cuda")
+    addr = (ctypes.c_uint64 * 2)(bufs[0].data_ptr(), bufs[1].data_ptr())
+    st = _lib.stream_ptr(d2.device)
+    for s_ in range(W):
+        _lib.check(lib.dicp_nn_push_keys_f32(_lib.ptr(d2[s_]), _lib.ptr(idx[s_]), offs[s_], count, addr, 2, s_ % 2,
+                                             _lib.ptr(spare), st), "push")
+    want = torch.stack([pack_keys(d2[s_], idx[s_], offs[s_]) for s_ in range(W)]).min(0).values
+    want_idx, want_d2 = unpack_keys(want)
+    assert (spare == -1).all()                                 # the "next iteration" buffer was reset
+    for b in bufs:
+        assert torch.equal(b, want)
+        out_i = torch.empty((count,), dtype=torch.int32, device="cuda")
+        out_d = torch.empty((count,), dtype=torch.float32, device="cuda")
+        _lib.check(lib.dicp_nn_unpack_keys_f32(_lib.ptr(b), count, _lib.ptr(out_i), _lib.ptr(out_d), st), "unpack")
+        assert torch.equal(out_i, want_idx) and torch.equal(out_d, want_d2)
+
+
 def test_search_hook_failure_surfaces_as_the_python_exception():
     from oracle.dicp_oracle import make_wavy_pair
 

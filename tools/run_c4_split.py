@@ -1,7 +1,7 @@
 """BASELINE.json config 4 (one 130k x 130k pair, pt2pl, forward + backward, 10 iterations) with the
 TARGETS split over the GPUs of one box (dicp_b200.parallel.SplitTargetSearch):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/run_c4_split.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/run_c4_split.py [auto|nccl|peer]
 
 Rank 0 also runs the plain single-GPU brute-force call and checks that the split run reproduces
 it bit for bit; timing: CUDA events, barrier + synchronize on both sides, max over ranks."""
@@ -60,8 +60,10 @@ def timed(search, reps=5, warm=2):
     return float(ms), out
 
 
-ms_split, (T_split, g_split) = timed(SplitTargetSearch())
-line = {"config": "C4: 1 pair x 130000 x 130000, pt2pl, cauchy(0.5)+trim(2.0), fp32, 10 it, forward + backward",
+transport = sys.argv[1] if len(sys.argv) > 1 else "auto"
+search = SplitTargetSearch(transport=transport)
+ms_split, (T_split, g_split) = timed(search)
+line = {"transport": search.used_transport, "config": "C4: 1 pair x 130000 x 130000, pt2pl, cauchy(0.5)+trim(2.0), fp32, 10 it, forward + backward",
         "n_gpus": world, "split_targets_ms": ms_split, "pairs_per_s": 1e3 / ms_split,
         "nn_tflops_algorithmic": 8.0 * 130000.0 ** 2 * 10 / (ms_split * 1e-3) / 1e12}
 if rank == 0:
