@@ -198,6 +198,9 @@ def roofline_nn(src, tgt, pk):
             "traffic": 201.7e6 if (N, n, m) == (256, 16384, 16384) else None, "ms_per_launch": sec * 1e3,
             "executed_tflops": executed, "frac_executed": executed / peak,
             "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],
+            # context: a loop of independent FFMAs issues at 1.13 cycles per warp instruction and scheduler on this part
+            # (tools/ubench_fp32.cu, profiles/r01_nn_tuning.md), i.e. 88 % of the nominal peak is the most FFMA code reaches
+            "ffma_issue_peak_measured": peak / 1.13, "frac_executed_of_ffma_issue_peak": executed / (peak / 1.13),
             "flop_per_pair_eval": {"algorithmic": 8, "executed": 6}, "units_per_launch": evals}, idx
 
 

@@ -580,12 +580,21 @@ static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_
 // exact fallback for the fp32 filter's ambiguous queries: direct-form rescan of the per-pair lists.
 // One warp per CTA (a pair rarely lists more than a few dozen queries), the target range split over
 // blockIdx.z so that the whole machine works on it; splits merge through atomicMin on fb_key.
-constexpr int NN_FB_Q = 2;
+#ifndef NN_FB_QUERIES
+#define NN_FB_QUERIES 2
+#endif
+#ifndef NN_FB_TILES_PER_SPLIT
+#define NN_FB_TILES_PER_SPLIT 4
+#endif
+#ifndef NN_FB_MAX_SPLITS
+#define NN_FB_MAX_SPLITS 8
+#endif
+constexpr int NN_FB_Q = NN_FB_QUERIES;
 static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const float* q, const double* state, const float4* packed, int n, int m_pad,
                            int32_t* idx_out, float* d2_out, const int* stop_flag) {
   const int tiles_total = (m_pad + NN_TILE - 1) / NN_TILE;
-  int fs = tiles_total / 4;
-  if (fs > 8) fs = 8;
+  int fs = tiles_total / NN_FB_TILES_PER_SPLIT;
+  if (fs > NN_FB_MAX_SPLITS) fs = NN_FB_MAX_SPLITS;
   if (fs < 1) fs = 1;
   const int tps = (tiles_total + fs - 1) / fs;
   fs = (tiles_total + tps - 1) / tps;
