@@ -8,7 +8,7 @@ A single huge pair does not shard over pairs; `SplitTargetSearch` splits its TAR
 (SURVEY.md §8 f-3): every rank scans its slice of the target cloud for all queries and one
 MIN all-reduce per iteration over packed (distance, index) keys merges the slices — the one
 place on the path with a real exchange step."""
-from typing import Iterable, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist

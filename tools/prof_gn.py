@@ -1,5 +1,4 @@
 """Time the GN accumulate stage (dicp_gn_accumulate_f32) and the full backward on C3-shaped data."""
-import ctypes
 import os
 import sys
 
@@ -8,7 +7,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from dicp_b200 import _functions, _lib  # noqa: E402
+from dicp_b200 import _functions  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 pk = bench.peaks()
