@@ -52,3 +52,21 @@ def test_product_fails_loudly_without_cuda():
     from dICP.nn import nn
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         nn(differentiable=False).find_nn(torch.zeros(4, 3), torch.zeros(4, 3))
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/dicp_b200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types) and a
+    C program must link against the library through it (dicp_version needs no device)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "dicp_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %zu\\n", dicp_version(), dicp_icp_workspace_bytes(2, 100, 100, 4)); return 0; }\n')
+    exe = tmp_path / "use_header"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-ldicp_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[0]) >= 100 and int(out[1]) > 0
