@@ -18,12 +18,13 @@
 // among all *other* chunks.  If that runner-up is further away than a rigorous rounding bound
 // (nn_filter_margin), the nearest neighbour must be inside the best chunk and is found there
 // with the exact direct-form distance on the ORIGINAL coordinates; otherwise the query is appended
-// to its pair's list, and the listed queries are rescanned exactly by the direct-form kernel
-// (nn_scan_kernel<float,.,true>, same tiling, original records).  Either way the result is the
+// to its pair's list together with the threshold (best filter value + margin) below which a chunk can
+// still hold the nearest neighbour, and nn_fallback_filter_kernel re-runs the filter for the listed
+// queries and evaluates exactly every chunk under the threshold.  Either way the result is the
 // direct-form fp32 argmin with torch.argmin's first-minimum tie-break.  On the benchmark clouds
 // (extent +-20 m) about 0.3 % of the queries take the fallback, wherever the clouds sit (without the
 // translation a cloud 1 km from the origin sent every query to the fallback: 10x slower).
-// fp64 (nn_scan_kernel<double,.,false>): plain direct-form scan, used by the fp64 parity tests.
+// fp64 (nn_scan_kernel<double,.>): plain direct-form scan, used by the fp64 parity tests.
 //
 // The target range is split over blockIdx.z when that is needed to fill 148 SMs or to keep the
 // tail wave short; partial (d2, idx) results are merged in split order (earlier split wins ties).
@@ -156,28 +157,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 constexpr int NN_THREADS = 128;   // fp64 scan
-constexpr int NN_FB_THREADS = 32; // fp32 exact fallback: one warp per CTA, few queries per pair
 constexpr int NN_TILE = 512;      // records per shared-memory stage
 
-// Exact direct-form scan over (x,y,z,.) records.  LIST == false: every query of the pair (fp64 path).
-// LIST == true: only the queries listed in qlist[b, 0 .. qcount[b]) (the fp32 filter's ambiguous queries;
-// `packed` is then the array of ORIGINAL fp32 records).
-template <typename T, int Q, bool LIST, int THREADS>
+// Exact direct-form scan over (x,y,z,.) records: every query of the pair (the fp64 path).
+template <typename T, int Q, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
                const typename Vec4<T>::type* __restrict__ packed, int n, int m_pad, int tiles_per_split,
                int32_t* __restrict__ idx_out, T* __restrict__ d2_out, T* __restrict__ part_d2,
-               int32_t* __restrict__ part_idx, const unsigned int* __restrict__ qcount, const int32_t* __restrict__ qlist,
-               int qcap, unsigned long long* __restrict__ qkey, const int* __restrict__ stop_flag) {
+               int32_t* __restrict__ part_idx, const int* __restrict__ stop_flag) {
   constexpr int NN_THREADS = THREADS;
   typedef typename Vec4<T>::type V4;
   if (stop_flag != nullptr && *stop_flag != 0) return;
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
-  int nq = n;                              // number of queries this pair has for this launch
-  if (LIST) {
-    nq = (int)min(qcount[b], (unsigned int)qcap);
-  }
   __shared__ __align__(16) V4 tile[2][NN_TILE];
   const int split = blockIdx.z;
   const int N = gridDim.y;
@@ -192,18 +185,13 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
 #pragma unroll
     for (int i = 0; i < 3; ++i) r[i] = (T)rec[ST_R + i];
   }
-  // LIST: the grid's x extent is small and fixed (the list length is only known on the device), so a
-  // CTA walks the list in strides; otherwise the loop body runs once
-  for (int qblk = blockIdx.x * (NN_THREADS * Q); qblk < nq; qblk += gridDim.x * (NN_THREADS * Q)) {
   T x[Q][3], best[Q];
-  int bchunk[Q], qi[Q];
-  const int q0 = qblk + tid;
+  int bchunk[Q];
+  const int q0 = blockIdx.x * (NN_THREADS * Q) + tid;
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
     int i = q0 + k * NN_THREADS;
-    if (i >= nq) i = nq - 1;
-    if (LIST) i = qlist[(size_t)b * qcap + i];
-    qi[k] = i;
+    if (i >= n) i = n - 1;
     const T* p = q + ((size_t)b * n + i) * 3;
     T pv[3] = {p[0], p[1], p[2]};
     if (state != nullptr) {
@@ -260,8 +248,8 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
   // refine: the exact index inside the winning chunk (bit-identical arithmetic)
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
-    if (q0 + k * NN_THREADS >= nq) continue;
-    const int i = qi[k];
+    const int i = q0 + k * NN_THREADS;
+    if (i >= n) continue;
     int found = -1;
     const V4* ch = tg + (size_t)bchunk[k] * NN_CHUNK;
     if (t_begin < t_end) {
@@ -274,12 +262,7 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
     }
     if (found < 0) found = 0;
     const size_t o = (size_t)b * n + i;
-    if (LIST) {
-      // target splits of the fallback merge through a 64-bit atomic minimum on (d2 bits, index):
-      // non-negative floats order like their bit patterns, so this is the lexicographic first minimum
-      if (t_begin < t_end)
-        atomicMin(&qkey[o], ((unsigned long long)__float_as_uint((float)best[k]) << 32) | (unsigned int)found);
-    } else if (part_d2 == nullptr) {
+    if (part_d2 == nullptr) {
       idx_out[o] = found;
       if (d2_out != nullptr) d2_out[o] = best[k];
     } else {
@@ -287,7 +270,6 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
       part_idx[((size_t)split * N) * n + o] = found;
     }
   }
-  }   // query-block loop
 }
 
 // ---------------------------------------------------------------------------------------
@@ -336,7 +318,7 @@ __global__ void __launch_bounds__(NNF_THREADS, NNF_MINB)
 nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n,
                    int m_pad, int tiles_per_split, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
                    float* __restrict__ part_d2, int32_t* __restrict__ part_idx, unsigned int* __restrict__ fb_count,
-                   int32_t* __restrict__ fb_list, int fb_cap, unsigned long long* __restrict__ fb_key,
+                   int32_t* __restrict__ fb_list, float* __restrict__ fb_thr, int fb_cap, unsigned long long* __restrict__ fb_key,
                    const int* __restrict__ stop_flag) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   __shared__ __align__(16) float4 tile[2][NNF_TILE];
@@ -446,9 +428,16 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
     int found = 0;
     float bd = INF;
     if (t_begin < t_end) {
-      if (!(second[k] - best[k] > nn_filter_margin(x[k][0], x[k][1], x[k][2], best[k]))) {
+      const float margin = nn_filter_margin(x[k][0], x[k][1], x[k][2], best[k]);
+      if (!(second[k] - best[k] > margin)) {
         const unsigned int slot = atomicAdd(&fb_count[b], 1u);
-        if (slot < (unsigned int)fb_cap) fb_list[(size_t)b * fb_cap + slot] = i;
+        if (slot < (unsigned int)fb_cap) {
+          fb_list[(size_t)b * fb_cap + slot] = i;
+          // the true nearest neighbour's filter value is at most best + margin: the fallback only has to
+          // look into chunks whose filter minimum is below this threshold (slack for rounding the sum)
+          const float thr = best[k] + margin;
+          fb_thr[(size_t)b * fb_cap + slot] = thr + 4.8e-7f * fabsf(thr);
+        }
         fb_key[o] = 0xffffffffffffffffull;
       }
       float xo[3];
@@ -468,6 +457,148 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
       part_d2[((size_t)split * N) * n + o] = bd;
       part_idx[((size_t)split * N) * n + o] = found;
     }
+  }
+}
+
+// Exact fallback for the filter's ambiguous queries (fp32).  The scan kernel lists each of them with the
+// threshold  thr = (its best filter value) + (its error margin):  the direct-form nearest neighbour can only
+// lie in a 32-record chunk whose filter minimum is <= thr (nn_filter_margin).  One warp per CTA walks a pair's
+// list: it runs the same three-FFMA filter over its share of the target range, queues every (query, chunk)
+// candidate in shared memory, and evaluates the queued chunks with the exact direct-form distance on the
+// ORIGINAL records, one candidate per lane.  Results merge across chunks, CTAs and target splits through a
+// 64-bit atomicMin on (d2 bits, index): the lexicographic first minimum, as torch.argmin.  Typically 2-3
+// chunks per query are candidates, so this costs half of an exact rescan of all targets.
+constexpr int FBF_THREADS = 32;
+constexpr int FBF_Q = 2;
+#ifndef FBF_TILE_RECORDS
+#define FBF_TILE_RECORDS 512
+#endif
+constexpr int FBF_TILE = FBF_TILE_RECORDS;
+constexpr int FBF_QUEUE = 512;
+
+__global__ void __launch_bounds__(FBF_THREADS)
+nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict__ state, const float4* __restrict__ packed, int n, int m_pad,
+                          int tiles_per_split, const unsigned int* __restrict__ qcount, const int32_t* __restrict__ qlist,
+                          const float* __restrict__ qthr, int qcap, unsigned long long* __restrict__ qkey,
+                          const int* __restrict__ stop_flag) {
+  if (stop_flag != nullptr && *stop_flag != 0) return;
+  __shared__ __align__(16) float4 tile[2][FBF_TILE];
+  __shared__ float qx[FBF_THREADS * FBF_Q][3];
+  __shared__ int qid[FBF_THREADS * FBF_Q];
+  __shared__ int queue[FBF_QUEUE];
+  const int lane = threadIdx.x;
+  const int b = blockIdx.y;
+  const int split = blockIdx.z;
+  const int N = gridDim.y;
+  const int nq = (int)min(qcount[b], (unsigned int)qcap);
+  const float4* tg = packed + (size_t)b * m_pad;
+  const float4* tg_orig = nn_orig_records(packed, N, m_pad) + (size_t)b * m_pad;
+  const float4 ctr = nn_centers(packed, N, m_pad)[b];
+  const float INF = Sentinel<float>::inf();
+  const int tiles_total = (m_pad + FBF_TILE - 1) / FBF_TILE;
+  const int t_begin = split * tiles_per_split;
+  const int t_end = min(t_begin + tiles_per_split, tiles_total);
+  if (t_begin >= t_end) return;
+
+  // evaluates the queued (query, chunk) candidates exactly, one per lane
+  auto flush = [&](int count) {
+    __syncwarp();
+    for (int t = lane; t < count; t += FBF_THREADS) {
+      const int e = queue[t];
+      const int slot = e & (FBF_THREADS * FBF_Q - 1), chunk = e >> 6;
+      const float x0 = qx[slot][0], x1 = qx[slot][1], x2 = qx[slot][2];
+      const float4* ch = tg_orig + (size_t)chunk * NN_CHUNK;
+      float bd = INF;
+      int found = chunk * NN_CHUNK;
+#pragma unroll 4
+      for (int j = 0; j < NN_CHUNK; ++j) {
+        const float4 y = ch[j];
+        const float d = dist2<float>(x0, x1, x2, y.x, y.y, y.z);
+        if (d < bd) { bd = d; found = chunk * NN_CHUNK + j; }
+      }
+      atomicMin(&qkey[(size_t)b * n + qid[slot]], ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned int)found);
+    }
+    __syncwarp();
+  };
+  static_assert(FBF_THREADS * FBF_Q == 64, "queue entries keep the query slot in 6 bits");
+
+  for (int qblk = blockIdx.x * (FBF_THREADS * FBF_Q); qblk < nq; qblk += gridDim.x * (FBF_THREADS * FBF_Q)) {
+    float x[FBF_Q][3], thr[FBF_Q];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < FBF_Q; ++k) {
+      const int s = qblk + k * FBF_THREADS + lane;
+      const bool valid = s < nq;
+      const int sc = valid ? s : nq - 1;
+      const int i = qlist[(size_t)b * qcap + sc];
+      thr[k] = valid ? qthr[(size_t)b * qcap + sc] : -INF;          // -inf: never a candidate
+      // the query in the target frame, with the arithmetic of the scan kernel (ICP.py:137)
+      const float* p = q + ((size_t)b * n + i) * 3;
+      const float pv[3] = {p[0], p[1], p[2]};
+      float xo[3];
+      if (state != nullptr) {
+        const double* rec = state + (size_t)b * ST_STRIDE;
+        float C[9], a[3];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) C[c] = (float)rec[ST_C + c];
+        rotate(C, pv, a);
+        xo[0] = a[0] + (float)rec[ST_R]; xo[1] = a[1] + (float)rec[ST_R + 1]; xo[2] = a[2] + (float)rec[ST_R + 2];
+      } else {
+        xo[0] = pv[0]; xo[1] = pv[1]; xo[2] = pv[2];
+      }
+      x[k][0] = xo[0] - ctr.x; x[k][1] = xo[1] - ctr.y; x[k][2] = xo[2] - ctr.z;
+      const int slot = k * FBF_THREADS + lane;
+      qx[slot][0] = xo[0]; qx[slot][1] = xo[1]; qx[slot][2] = xo[2];
+      qid[slot] = i;
+    }
+    __syncwarp();
+
+    auto issue_tile = [&](int t, int buf) {
+      const int start = t * FBF_TILE;
+      const int cnt = min(FBF_TILE, m_pad - start);
+      for (int u = lane; u < cnt; u += FBF_THREADS) cp_async16(&tile[buf][u], tg + start + u);
+      cp_async_commit();
+    };
+    int queued = 0;                          // warp-uniform
+    issue_tile(t_begin, 0);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int buf = (t - t_begin) & 1;
+      if (t + 1 < t_end) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncwarp();
+      const int start = t * FBF_TILE;
+      const int nchunks = min(FBF_TILE, m_pad - start) / NN_CHUNK;
+      for (int c = 0; c < nchunks; ++c) {
+        float cm[FBF_Q];
+#pragma unroll
+        for (int k = 0; k < FBF_Q; ++k) cm[k] = INF;
+        const float4* ch = &tile[buf][c * NN_CHUNK];
+#pragma unroll
+        for (int j = 0; j < NN_CHUNK; j += 2) {
+          const float4 a0 = ch[j], a1 = ch[j + 1];
+#pragma unroll
+          for (int k = 0; k < FBF_Q; ++k) {
+            float v0 = __fmaf_rn(x[k][2], a0.z, a0.w), v1 = __fmaf_rn(x[k][2], a1.z, a1.w);
+            v0 = __fmaf_rn(x[k][1], a0.y, v0); v1 = __fmaf_rn(x[k][1], a1.y, v1);
+            v0 = __fmaf_rn(x[k][0], a0.x, v0); v1 = __fmaf_rn(x[k][0], a1.x, v1);
+            cm[k] = min3(cm[k], v0, v1);
+          }
+        }
+        const int chunk = start / NN_CHUNK + c;
+#pragma unroll
+        for (int k = 0; k < FBF_Q; ++k) {
+          const bool hit = !(cm[k] > thr[k]);
+          const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+          if (mask != 0u) {
+            if (hit) queue[queued + __popc(mask & ((1u << lane) - 1u))] = (chunk << 6) | (k * FBF_THREADS + lane);
+            queued += __popc(mask);
+            if (queued > FBF_QUEUE - FBF_THREADS) { flush(queued); queued = 0; }
+          }
+        }
+      }
+      __syncwarp();                         // everybody is done with tile[buf] before it is refilled
+    }
+    flush(queued);
   }
 }
 
@@ -537,12 +668,12 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
 }
 
 // workspace of one search: [split partials d2 | split partials idx] [fallback counter] [fallback list]
-struct NNWorkspace { void* part_d2; int32_t* part_idx; unsigned int* fb_count; int32_t* fb_list; int fb_cap; unsigned long long* fb_key; size_t total; };
+struct NNWorkspace { void* part_d2; int32_t* part_idx; unsigned int* fb_count; int32_t* fb_list; float* fb_thr; int fb_cap; unsigned long long* fb_key; size_t total; };
 static NNWorkspace nn_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size) {
   const NNPlan p = nn_plan(N, n, m, elem_size);
   Arena ar(ws, ws_bytes);
   NNWorkspace w;
-  w.part_d2 = nullptr; w.part_idx = nullptr; w.fb_count = nullptr; w.fb_list = nullptr; w.fb_key = nullptr;
+  w.part_d2 = nullptr; w.part_idx = nullptr; w.fb_count = nullptr; w.fb_list = nullptr; w.fb_thr = nullptr; w.fb_key = nullptr;
   if (p.nsplit > 1) {
     w.part_d2 = ar.take<char>((size_t)p.nsplit * N * n * elem_size);
     w.part_idx = ar.take<int32_t>((size_t)p.nsplit * N * n);
@@ -552,6 +683,7 @@ static NNWorkspace nn_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, 
     w.fb_cap = n * p.nsplit;                                       // every (query, split) can flag at most once
     w.fb_count = ar.take<unsigned int>(N);                         // per pair
     w.fb_list = ar.take<int32_t>((size_t)N * w.fb_cap);            // per pair: query indices
+    w.fb_thr = ar.take<float>((size_t)N * w.fb_cap);               // per listed query: filter threshold of its candidate chunks
     w.fb_key = ar.take<unsigned long long>((size_t)N * n);         // per query: (d2 bits << 32 | index) of the exact rescan
   }
   w.total = ar.off;
@@ -565,34 +697,30 @@ static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_
   dim3 grid(p.gx, N, p.nsplit);
   DICP_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(unsigned int) * N, st));
   nn_scan_f32_kernel<8><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
-                                                         w.part_idx, w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
+                                                         w.part_idx, w.fb_count, w.fb_list, w.fb_thr, w.fb_cap, w.fb_key, stop_flag);
   DICP_LAUNCH_CHECK();
   return 0;
 }
 static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_t st, const double* q, const double* state, const double4* packed,
                        int n, int m_pad, int32_t* idx_out, double* d2_out, const int* stop_flag) {
   dim3 grid(p.gx, N, p.nsplit);
-  nn_scan_kernel<double, 2, false, NN_THREADS><<<grid, NN_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out,
-                                                                            (double*)w.part_d2, w.part_idx, nullptr, nullptr, 0, nullptr, stop_flag);
+  nn_scan_kernel<double, 2, NN_THREADS><<<grid, NN_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out,
+                                                                     (double*)w.part_d2, w.part_idx, stop_flag);
   DICP_LAUNCH_CHECK();
   return 0;
 }
-// exact fallback for the fp32 filter's ambiguous queries: direct-form rescan of the per-pair lists.
-// One warp per CTA (a pair rarely lists more than a few dozen queries), the target range split over
-// blockIdx.z so that the whole machine works on it; splits merge through atomicMin on fb_key.
-#ifndef NN_FB_QUERIES
-#define NN_FB_QUERIES 2
-#endif
+// exact fallback for the fp32 filter's ambiguous queries (nn_fallback_filter_kernel): one warp per CTA (a pair
+// rarely lists more than a few dozen queries), the target range split over blockIdx.z so that the whole
+// machine works on it; candidates merge through atomicMin on fb_key.
 #ifndef NN_FB_TILES_PER_SPLIT
 #define NN_FB_TILES_PER_SPLIT 4
 #endif
 #ifndef NN_FB_MAX_SPLITS
 #define NN_FB_MAX_SPLITS 8
 #endif
-constexpr int NN_FB_Q = NN_FB_QUERIES;
 static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const float* q, const double* state, const float4* packed, int n, int m_pad,
                            int32_t* idx_out, float* d2_out, const int* stop_flag) {
-  const int tiles_total = (m_pad + NN_TILE - 1) / NN_TILE;
+  const int tiles_total = (m_pad + FBF_TILE - 1) / FBF_TILE;
   int fs = tiles_total / NN_FB_TILES_PER_SPLIT;
   if (fs > NN_FB_MAX_SPLITS) fs = NN_FB_MAX_SPLITS;
   if (fs < 1) fs = 1;
@@ -600,13 +728,12 @@ static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const f
   fs = (tiles_total + tps - 1) / tps;
   // CTAs stride over the lists (their lengths are only known on the device).  Few CTAs per pair when
   // there are many pairs (empty CTAs are not free), enough to fill the machine when there are few.
-  const int gx_cap = (w.fb_cap + NN_FB_THREADS * NN_FB_Q - 1) / (NN_FB_THREADS * NN_FB_Q);
+  const int gx_cap = (w.fb_cap + FBF_THREADS * FBF_Q - 1) / (FBF_THREADS * FBF_Q);
   int gx = (148 * 8 + N * fs - 1) / (N * fs);
   if (gx < 4) gx = 4;
   if (gx > gx_cap) gx = gx_cap;
   dim3 grid(gx, N, fs);
-  nn_scan_kernel<float, NN_FB_Q, true, NN_FB_THREADS><<<grid, NN_FB_THREADS, 0, st>>>(q, state, nn_orig_records(packed, N, m_pad), n, m_pad, tps, idx_out, d2_out, nullptr, nullptr,
-                                                                                      w.fb_count, w.fb_list, w.fb_cap, w.fb_key, stop_flag);
+  nn_fallback_filter_kernel<<<grid, FBF_THREADS, 0, st>>>(q, state, packed, n, m_pad, tps, w.fb_count, w.fb_list, w.fb_thr, w.fb_cap, w.fb_key, stop_flag);
   DICP_LAUNCH_CHECK();
   dim3 ugrid(1, N);
   nn_fallback_unpack_kernel<<<ugrid, 256, 0, st>>>(w.fb_count, w.fb_list, w.fb_cap, n, w.fb_key, idx_out, d2_out, stop_flag);
