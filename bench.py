@@ -101,8 +101,8 @@ class ClockSampler:
 
 def make_batch(n_pairs, first_pair, dtype=torch.float32):
     """seed = 1000*cfg_id + first pair index of the chunk (cfg_id 3)."""
-    from oracle.dicp_oracle import make_wavy_pair      # input generator only
-    return make_wavy_pair(n_pairs, NPTS, NPTS, seed=3000 + first_pair, dtype=dtype, with_normals=True)
+    from dicp_b200.synthetic import surface_pairs
+    return surface_pairs(n_pairs, NPTS, NPTS, seed=3000 + first_pair, dtype=dtype, with_normals=True)
 
 
 def learning_loss(res, theta):

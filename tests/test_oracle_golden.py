@@ -201,3 +201,14 @@ def test_kabsch_oracle_recovers_3d_motion():
     assert (T[:3, :3] - R).abs().max() < 1e-10 and (T[:3, 3] - t).abs().max() < 1e-10
     _, T_lit, _ = kabsch_icp(P, Q, torch.eye(4, dtype=torch.float64), 30, 1e-24, literal=True)
     assert (T_lit[:3, :3] - R).abs().max() > 1e-3
+
+
+def test_product_side_input_generator_equals_the_oracle_side_one():
+    """bench.py and the tools draw their synthetic clouds from dicp_b200.synthetic (the product path must not
+    import oracle/); the parity tests draw theirs from the oracle module.  Same numbers, bit for bit."""
+    from dicp_b200.synthetic import surface_pairs
+    from oracle.dicp_oracle import make_wavy_pair
+    for n_pairs, n, m, seed, dtype, normals in ((3, 100, 80, 5, torch.float32, True), (2, 50, 70, 9, torch.float64, False)):
+        a = surface_pairs(n_pairs, n, m, seed, dtype=dtype, with_normals=normals, extent=33.0)
+        b = make_wavy_pair(n_pairs, n, m, seed, dtype=dtype, with_normals=normals, extent=33.0)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dICP.ICP import ICP  # noqa: E402
 from dicp_b200.parallel import SplitTargetSearch  # noqa: E402
-from oracle.dicp_oracle import make_wavy_pair  # noqa: E402  (input generator only)
+from dicp_b200.synthetic import surface_pairs as make_wavy_pair  # noqa: E402
 
 rank = int(os.environ.get("RANK", 0))
 world = int(os.environ.get("WORLD_SIZE", 1))

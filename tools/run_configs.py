@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dICP.ICP import ICP  # noqa: E402
-from oracle.dicp_oracle import make_wavy_pair  # noqa: E402  (input generator only)
+from dicp_b200.synthetic import surface_pairs as make_wavy_pair  # noqa: E402
 
 
 def timed(fn, reps=5, warm=2):
