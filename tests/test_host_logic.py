@@ -64,3 +64,23 @@ def test_input_validation_happens_before_any_device_work():
         icp.icp(s, t.double(), T0)
     with pytest.raises(AssertionError):
         icp.icp(s, t[:, :, :3], T0)                                   # pt2pl needs normals
+
+
+def test_loss_class_matches_reference_known_answers():
+    """dicp_b200.loss.loss (the public mirror of dICP/loss.py:3-58, plain tensor math on the caller's device) on the
+    golden errors: Huber / Cauchy / trim, soft and hard, 3-D and 2-D inputs.  The reference's hard trim on a 2-D
+    input returns an accidental (n,n) broadcast (loss.py:46-58); every row of it equals the (n,) answer."""
+    from dicp_b200.loss import loss
+    g = np.load(os.path.join(HERE, "golden", "loss_known_answers.npz"))
+    for name, metric in (("huber", 1.3), ("cauchy", 0.7), ("trim", 1.9)):
+        for diff in (True, False):
+            L = loss(name=name, metric=metric, differentiable=diff, tanh_steepness=5.0)
+            for key in ("e3", "e1", "e2d"):
+                got = L.get_weight(torch.from_numpy(g[key])).numpy()
+                want = g["%s_%d_%s" % (name, diff, key)]
+                if want.ndim == 2 and got.ndim == 1 and want.shape == (got.shape[0], got.shape[0]):
+                    assert np.allclose(want, np.broadcast_to(got, want.shape), rtol=1e-12, atol=1e-15), (name, diff, key)
+                else:
+                    assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12, atol=1e-15), (name, diff, key)
+    with pytest.raises(ValueError):
+        loss(name="tukey").get_weight(torch.zeros(3, 3))                # loss.py:19
