@@ -285,7 +285,21 @@ constexpr int NNF_THREADS = 128;
 #define NNF_MINB 5
 #endif
 #ifndef NNF_IL
-#define NNF_IL 4
+#define NNF_IL 8
+#endif
+#ifndef NNF_ORDER
+#define NNF_ORDER 1
+#endif
+#ifndef NNF_XQUAD
+#define NNF_XQUAD 1
+#endif
+#ifndef NNF_SWAP
+#define NNF_SWAP 0
+#endif
+#if NNF_SWAP
+#define NNF_FMA(xv, av, cv) __fmaf_rn(av, xv, cv)
+#else
+#define NNF_FMA(xv, av, cv) __fmaf_rn(xv, av, cv)
 #endif
 constexpr int NNF_TILE = NNF_TILE_RECORDS;     // records per shared-memory stage (16 KB; two stages, 5 CTAs per SM)
 
@@ -359,6 +373,30 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
     x[k][0] = xo[0] - ctr.x; x[k][1] = xo[1] - ctr.y; x[k][2] = xo[2] - ctr.z;
     best[k] = INF; second[k] = INF; bchunk[k] = 0;
   }
+#if NNF_XQUAD
+  // Round trip of (x', best) through shared memory with a 128-bit load: the load's destination is an aligned
+  // register quad, which pins x'_0, x'_1, x'_2 of every query to register banks 0, 1, 2 for the whole scan.
+  static_assert(NNF_TILE >= NNF_THREADS * Q, "the second tile buffer stages the queries");
+#pragma unroll
+#ifndef NNF_XROT
+#define NNF_XROT 3
+#endif
+  // lane order inside the quad: component c of a record sits in bank c (records also arrive by LDS.128), so the
+  // query components are rotated by NNF_XROT lanes to keep x'_c out of the bank of the record component it multiplies
+  for (int k = 0; k < Q; ++k) {
+    float l[4];
+    l[(0 + NNF_XROT) & 3] = x[k][0]; l[(1 + NNF_XROT) & 3] = x[k][1]; l[(2 + NNF_XROT) & 3] = x[k][2]; l[(3 + NNF_XROT) & 3] = best[k];
+    tile[1][k * NNF_THREADS + tid] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    const unsigned int addr = (unsigned int)__cvta_generic_to_shared(&tile[1][k * NNF_THREADS + tid]);
+    float l[4];
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l[0]), "=f"(l[1]), "=f"(l[2]), "=f"(l[3]) : "r"(addr));
+    x[k][0] = l[(0 + NNF_XROT) & 3]; x[k][1] = l[(1 + NNF_XROT) & 3]; x[k][2] = l[(2 + NNF_XROT) & 3]; best[k] = l[(3 + NNF_XROT) & 3];
+  }
+  __syncthreads();                               // before the first cp.async into tile[1]
+#endif
 
   const int tiles_total = (m_pad + NNF_TILE - 1) / NNF_TILE;
   const int t_begin = split * tiles_per_split;
@@ -392,18 +430,40 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
         float v[NNF_IL][Q];
 #pragma unroll
         for (int i = 0; i < NNF_IL; ++i) a[i] = ch[j + i];
+#if NNF_ORDER == 0
 #pragma unroll
         for (int i = 0; i < NNF_IL; ++i)
 #pragma unroll
-          for (int k = 0; k < Q; ++k) v[i][k] = __fmaf_rn(x[k][2], a[i].z, a[i].w);
+          for (int k = 0; k < Q; ++k) v[i][k] = NNF_FMA(x[k][2], a[i].z, a[i].w);
 #pragma unroll
         for (int i = 0; i < NNF_IL; ++i)
 #pragma unroll
-          for (int k = 0; k < Q; ++k) v[i][k] = __fmaf_rn(x[k][1], a[i].y, v[i][k]);
+          for (int k = 0; k < Q; ++k) v[i][k] = NNF_FMA(x[k][1], a[i].y, v[i][k]);
 #pragma unroll
         for (int i = 0; i < NNF_IL; ++i)
 #pragma unroll
-          for (int k = 0; k < Q; ++k) v[i][k] = __fmaf_rn(x[k][0], a[i].x, v[i][k]);
+          for (int k = 0; k < Q; ++k) v[i][k] = NNF_FMA(x[k][0], a[i].x, v[i][k]);
+#elif NNF_ORDER == 1
+#pragma unroll
+        for (int i = 0; i < NNF_IL; ++i) {
+#pragma unroll
+          for (int k = 0; k < Q; ++k) v[i][k] = NNF_FMA(x[k][2], a[i].z, a[i].w);
+#pragma unroll
+          for (int k = 0; k < Q; ++k) v[i][k] = NNF_FMA(x[k][1], a[i].y, v[i][k]);
+#pragma unroll
+          for (int k = 0; k < Q; ++k) v[i][k] = NNF_FMA(x[k][0], a[i].x, v[i][k]);
+        }
+#else
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+#pragma unroll
+          for (int i = 0; i < NNF_IL; ++i) v[i][k] = NNF_FMA(x[k][2], a[i].z, a[i].w);
+#pragma unroll
+          for (int i = 0; i < NNF_IL; ++i) v[i][k] = NNF_FMA(x[k][1], a[i].y, v[i][k]);
+#pragma unroll
+          for (int i = 0; i < NNF_IL; ++i) v[i][k] = NNF_FMA(x[k][0], a[i].x, v[i][k]);
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < NNF_IL; i += 2)
 #pragma unroll
