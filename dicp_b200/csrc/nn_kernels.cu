@@ -277,6 +277,9 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
+// Tuning knobs of the filter scan (profiles/r01_nn_tuning.md has the sweeps): records per shared-memory tile, CTAs per SM
+// the register budget allows, records interleaved per thread, loop nest of the FFMAs (0 component-major, 1 record-major,
+// 2 query-major), and whether / how the query components are pinned to the lanes of a register quad (NNF_XQUAD, NNF_XROT).
 constexpr int NNF_THREADS = 128;
 #ifndef NNF_TILE_RECORDS
 #define NNF_TILE_RECORDS 1024
@@ -293,14 +296,7 @@ constexpr int NNF_THREADS = 128;
 #ifndef NNF_XQUAD
 #define NNF_XQUAD 1
 #endif
-#ifndef NNF_SWAP
-#define NNF_SWAP 0
-#endif
-#if NNF_SWAP
-#define NNF_FMA(xv, av, cv) __fmaf_rn(av, xv, cv)
-#else
 #define NNF_FMA(xv, av, cv) __fmaf_rn(xv, av, cv)
-#endif
 constexpr int NNF_TILE = NNF_TILE_RECORDS;     // records per shared-memory stage (16 KB; two stages, 5 CTAs per SM)
 
 // Filter margin of one query, in the translated frame (x = x', y = y' below).  u = 2^-24.
