@@ -473,6 +473,45 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   return 0;
 }
 
+// stage API: the solve / update half of one iteration (ICP.py:200-217, 239) on the partial rows of the
+// accumulate stage: fixed-order sum, pivoted solve in double, exp-map update.  One thread per pair is enough.
+template <typename T>
+__global__ void solve_update_stage_kernel(const double* __restrict__ partials, int nblk, const double* __restrict__ C_r, int N, int dim,
+                                          double tolerance, T* __restrict__ delta, double* __restrict__ C_r_next,
+                                          uint8_t* __restrict__ below, int* __restrict__ singular) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= N) return;
+  double red[RED_N];
+  for (int v = 0; v < RED_N; ++v) {
+    double s = 0.0;
+    for (int j = 0; j < nblk; ++j) s += partials[((size_t)b * nblk + j) * RED_N + v];
+    red[v] = s;
+  }
+  double cur[ST_STRIDE], nxt[ST_STRIDE];
+  for (int i = 0; i < ST_STRIDE; ++i) { cur[i] = 0.0; nxt[i] = 0.0; }
+  for (int i = 0; i < 12; ++i) cur[i] = C_r[(size_t)b * 12 + i];          // ST_C = 0, ST_R = 9
+  cur[ST_ACTIVE] = 1.0;
+  double ni = 0.0, mr = 0.0;
+  PairOutcome out;
+  pair_update<T>(red, cur, nxt, 0, dim, true, tolerance, 0.0, &ni, &mr, out);
+  for (int i = 0; i < 6; ++i) delta[(size_t)b * 6 + i] = (T)out.delta[i];
+  for (int i = 0; i < 12; ++i) C_r_next[(size_t)b * 12 + i] = nxt[i];
+  if (below != nullptr) below[b] = out.below ? 1 : 0;
+  if (out.singular && singular != nullptr) atomicExch(singular, 1);
+}
+
+template <typename T>
+static int solve_update_api(const double* partials, int nblk, const double* C_r, int N, const dicp_params* p, T* delta,
+                            double* C_r_next, uint8_t* below, void* stream) {
+  DICP_CHECK_ARG(partials && C_r && p && delta && C_r_next, "null pointer");
+  DICP_CHECK_ARG(N >= 1 && nblk >= 1 && (p->dim == 2 || p->dim == 3), "bad sizes");
+  static_assert(ST_C == 0 && ST_R == 9, "the stage API copies (C, r) to the front of a state record");
+  solve_update_stage_kernel<T><<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(partials, nblk, C_r, N, p->dim, p->tolerance, delta,
+                                                                              C_r_next, below, nullptr);
+  DICP_LAUNCH_CHECK();
+  return 0;
+}
+
 // stage API: the loop's accumulate kernel in ONE launch on a bare [N,12] (C, r); the per-CTA partial
 // rows come back as they are (gn_update_kernel sums them in index order in the loop)
 template <typename T>
@@ -527,6 +566,14 @@ int dicp_icp_forward_hooked_f64(const double* source, const double* target, cons
   if (hook == nullptr) { dicp::set_error("dicp_icp_forward_hooked: null hook"); return DICP_ERR_ARG; }
   return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                         converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream, hook, user);
+}
+int dicp_solve_update_f32(const double* partials, int nblk, const double* C_r, int N, const dicp_params* params, float* delta,
+                          double* C_r_next, uint8_t* below_tolerance, void* stream) {
+  return dicp::solve_update_api<float>(partials, nblk, C_r, N, params, delta, C_r_next, below_tolerance, stream);
+}
+int dicp_solve_update_f64(const double* partials, int nblk, const double* C_r, int N, const dicp_params* params, double* delta,
+                          double* C_r_next, uint8_t* below_tolerance, void* stream) {
+  return dicp::solve_update_api<double>(partials, nblk, C_r, N, params, delta, C_r_next, below_tolerance, stream);
 }
 int dicp_gn_blocks_per_pair(int n) { return dicp::gn_blocks_per_pair(n); }
 size_t dicp_gn_rows_bytes(int N, int m, int elem_size) { return dicp::gn_rows_bytes(N, m, elem_size); }

@@ -226,6 +226,17 @@ DICP_API int dicp_gn_accumulate_f64(const double* source, const double* target, 
                            const double* C_r, int N, int n, int m, int S, const dicp_params* params,
                            double* weights_out, double* partials_out, void* stream);
 
+/* The other half of one iteration (ICP.py:200-217, 239): sums the partial rows of
+ * dicp_gn_accumulate_* in index order, solves A delta = -b (6x6, or 3x3 for dim 2, partial
+ * pivoting in double, +1e-12 on the diagonal), applies C+ = exp(phi^)^T C, r+ = r - rho.
+ * delta [N,6] in the compute type, C_r_next [N,12] doubles (row-major C+ then r+, rounded
+ * through the compute type like the loop's state), below_tolerance [N] (may be NULL):
+ * ||delta|| < params->tolerance.                                                          */
+DICP_API int dicp_solve_update_f32(const double* partials, int nblk, const double* C_r, int N, const dicp_params* params,
+                          float* delta, double* C_r_next, uint8_t* below_tolerance, void* stream);
+DICP_API int dicp_solve_update_f64(const double* partials, int nblk, const double* C_r, int N, const dicp_params* params,
+                          double* delta, double* C_r_next, uint8_t* below_tolerance, void* stream);
+
 /* ---- Kabsch / SVD point-to-point step: the per-point half of dICP/ICP.py:557-563 ----------
  * sums[b] = ( sum_i p_i (3), sum_i q_i (3), sum_i q_i p_i^T (9, row-major), pad ),  q_i = tgt[b, idx[b,i], :3]
  * from which the centroids and the cross-covariance W = M/n - q_mean p_mean^T follow; the 3x3

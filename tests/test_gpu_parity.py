@@ -352,6 +352,19 @@ def test_gn_accumulate_stage_vs_oracle():
         A = A + A.transpose(1, 2) - torch.diag_embed(torch.diagonal(A, dim1=1, dim2=2))
         assert rel_err(A, A_ref) < tol
         assert (red[:, 29] == n).all() and (red[:, 30] == n).all()
+        # the other half of the iteration through its stage entry: delta = -A^-1 b, C+ = exp(phi^)^T C, r+ = r - rho
+        delta = torch.empty((N, 6), dtype=dt, device="cuda")
+        C_r_next = torch.empty((N, 12), dtype=torch.float64, device="cuda")
+        below = torch.empty((N,), dtype=torch.uint8, device="cuda")
+        rc = getattr(lib, "dicp_solve_update_" + _lib.suffix(dt))(_lib.ptr(part), nblk, _lib.ptr(C_r), N, ctypes.byref(p), _lib.ptr(delta),
+                                                                  _lib.ptr(C_r_next), _lib.ptr(below), st)
+        _lib.check(rc, "solve_update")
+        d_ref = fw["saved"]["delta"][0].reshape(N, 6)
+        assert rel_err(delta.double().cpu(), d_ref) < max(tol, 1e-10) * 50
+        C1 = C_r_next[:, :9].reshape(N, 3, 3).cpu()
+        r1 = C_r_next[:, 9:].cpu()
+        assert rel_err(C1, fw["saved"]["C_final"]) < max(tol, 1e-10) * 50 and rel_err(r1, fw["saved"]["r_final"].reshape(N, 3)) < max(tol, 1e-10) * 50
+        assert not below.any()
 
 
 # ---------------------------------------------------------------------------------------
