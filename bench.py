@@ -181,7 +181,7 @@ def roofline_nn(src, tgt, pk):
     ws = torch.empty(max(lib.dicp_nn_workspace_bytes(N, n, m, 4), 256), dtype=torch.uint8, device=dev)
     idx = torch.empty((N, n), dtype=torch.int32, device=dev)
     st = _lib.stream_ptr(dev)
-    _lib.check(lib.dicp_nn_pack_f32(_lib.ptr(tgt), N, m, 6, _lib.ptr(packed), st), "pack")
+    _lib.check(lib.dicp_nn_pack_f32(_lib.ptr(tgt), N, m, 6, None, _lib.ptr(packed), st), "pack")
 
     def launch():
         _lib.check(lib.dicp_nn_scan_f32(_lib.ptr(src), None, _lib.ptr(packed), N, n, m, _lib.ptr(idx), None, _lib.ptr(ws), ws.numel(), st), "scan")

@@ -14,9 +14,10 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def nn_argmin(x, y, return_d2=False, search="brute"):
+def nn_argmin(x, y, return_d2=False, search="brute", m_valid=None):
     """x (N,n,3), y (N,m,3|6) CUDA tensors -> idx (N,n) int32 [, d2 (N,n)] (nn.py:32-35).
-    search: 'brute' (tiled scan) or 'grid' (uniform grid, same result)."""
+    search: 'brute' (tiled scan) or 'grid' (uniform grid, same result).
+    m_valid (N,) int32 CUDA tensor or None: real row count of every target cloud of a padded batch."""
     require_cuda()
     lib = load_library()
     assert x.is_cuda and y.is_cuda and x.dtype == y.dtype
@@ -34,7 +35,7 @@ def nn_argmin(x, y, return_d2=False, search="brute"):
         name = "dicp_nn_argmin_" + sfx
         ws = _workspace(lib.dicp_nn_workspace_bytes(N, n, m, x.element_size()), x.device)
     with torch.cuda.device(x.device):
-        rc = getattr(lib, name)(ptr(x), ptr(y), N, n, m, S, ptr(idx), ptr(d2), ptr(ws), ws.numel(), stream_ptr(x.device))
+        rc = getattr(lib, name)(ptr(x), ptr(y), N, n, m, S, ptr(m_valid), ptr(idx), ptr(d2), ptr(ws), ws.numel(), stream_ptr(x.device))
     check(rc, name)
     return (idx, d2) if return_d2 else idx
 

@@ -47,9 +47,9 @@ _SIGNATURES = {
     "dicp_nn_grid_workspace_bytes": ([_I, _I, _I, _I], _Z),
 }
 for _s in ("f32", "f64"):
-    _SIGNATURES["dicp_nn_argmin_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
-    _SIGNATURES["dicp_nn_argmin_grid_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
-    _SIGNATURES["dicp_nn_pack_" + _s] = ([_P, _I, _I, _I, _P, _P], _I)
+    _SIGNATURES["dicp_nn_argmin_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P], _I)
+    _SIGNATURES["dicp_nn_argmin_grid_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P], _I)
+    _SIGNATURES["dicp_nn_pack_" + _s] = ([_P, _I, _I, _I, _P, _P, _P], _I)
     _SIGNATURES["dicp_nn_scan_" + _s] = ([_P, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_gather_rows_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)
     _SIGNATURES["dicp_gather_rows_bwd_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)

@@ -383,14 +383,14 @@ template int grid_search<float>(const float*, const double*, int, int, int, cons
 template int grid_search<double>(const double*, const double*, int, int, int, const GridWorkspace&, bool, int32_t*, double*, const int*, cudaStream_t);
 
 template <typename T>
-static int nn_argmin_grid_impl(const T* q, const T* tgt, int N, int n, int m, int S, int32_t* idx_out, T* d2_out, void* ws,
-                               size_t ws_bytes, void* stream) {
+static int nn_argmin_grid_impl(const T* q, const T* tgt, int N, int n, int m, int S, const int32_t* m_valid, int32_t* idx_out, T* d2_out,
+                               void* ws, size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(q && tgt && idx_out, "null pointer");
   DICP_CHECK_ARG(N >= 1 && N <= 65535 && n >= 1 && m >= 1 && (S == 3 || S == 6), "bad sizes");
   const GridWorkspace g = grid_ws_layout(ws, ws_bytes, N, n, m, sizeof(T));
   if (ws == nullptr || g.total > ws_bytes) { set_error("dicp_nn_argmin_grid: workspace too small"); return DICP_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = grid_build<T>(tgt, N, m, S, nullptr, g, st);
+  int rc = grid_build<T>(tgt, N, m, S, m_valid, g, st);
   if (rc) return rc;
   rc = grid_sort_queries<T>(q, nullptr, N, n, g, st);
   if (rc) return rc;
@@ -401,12 +401,12 @@ static int nn_argmin_grid_impl(const T* q, const T* tgt, int N, int n, int m, in
 
 extern "C" {
 size_t dicp_nn_grid_workspace_bytes(int N, int n, int m, int elem_size) { return dicp::grid_ws_layout(nullptr, 0, N, n, m, elem_size).total; }
-int dicp_nn_argmin_grid_f32(const float* q, const float* tgt, int N, int n, int m, int S, int32_t* idx_out, float* d2_out, void* ws,
-                            size_t ws_bytes, void* stream) {
-  return dicp::nn_argmin_grid_impl<float>(q, tgt, N, n, m, S, idx_out, d2_out, ws, ws_bytes, stream);
+int dicp_nn_argmin_grid_f32(const float* q, const float* tgt, int N, int n, int m, int S, const int32_t* m_valid, int32_t* idx_out,
+                            float* d2_out, void* ws, size_t ws_bytes, void* stream) {
+  return dicp::nn_argmin_grid_impl<float>(q, tgt, N, n, m, S, m_valid, idx_out, d2_out, ws, ws_bytes, stream);
 }
-int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, int n, int m, int S, int32_t* idx_out, double* d2_out, void* ws,
-                            size_t ws_bytes, void* stream) {
-  return dicp::nn_argmin_grid_impl<double>(q, tgt, N, n, m, S, idx_out, d2_out, ws, ws_bytes, stream);
+int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, int n, int m, int S, const int32_t* m_valid, int32_t* idx_out,
+                            double* d2_out, void* ws, size_t ws_bytes, void* stream) {
+  return dicp::nn_argmin_grid_impl<double>(q, tgt, N, n, m, S, m_valid, idx_out, d2_out, ws, ws_bytes, stream);
 }
 }

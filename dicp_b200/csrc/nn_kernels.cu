@@ -825,7 +825,7 @@ size_t nn_workspace_bytes(int N, int n, int m, int elem_size) {
 }
 
 template <typename T>
-static int nn_argmin_impl(const T* q, const T* tgt, int N, int n, int m, int S, int32_t* idx_out, T* d2_out,
+static int nn_argmin_impl(const T* q, const T* tgt, int N, int n, int m, int S, const int32_t* m_valid, int32_t* idx_out, T* d2_out,
                           void* ws, size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(q && tgt && idx_out, "null pointer");
   DICP_CHECK_ARG(N >= 1 && n >= 1 && m >= 1, "N, n, m must be >= 1");
@@ -835,7 +835,7 @@ static int nn_argmin_impl(const T* q, const T* tgt, int N, int n, int m, int S, 
   Arena ar(ws, ws_bytes);
   typedef typename Vec4<T>::type V4;
   V4* packed = (V4*)ar.take<char>(nn_packed_bytes(N, m, sizeof(T)));
-  int rc = nn_pack_targets<T>(tgt, N, m, S, nullptr, packed, st);
+  int rc = nn_pack_targets<T>(tgt, N, m, S, m_valid, packed, st);
   if (rc) return rc;
   return nn_search<T>(q, nullptr, packed, N, n, m, idx_out, d2_out, nullptr, (char*)ws + ar.off, ws_bytes - ar.off, st);
 }
@@ -909,22 +909,22 @@ static int grid_for(size_t count) {
 
 extern "C" {
 size_t dicp_nn_workspace_bytes(int N, int n, int m, int elem_size) { return dicp::nn_workspace_bytes(N, n, m, elem_size); }
-int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, int m, int S, int32_t* idx_out, float* d2_out,
-                       void* ws, size_t ws_bytes, void* stream) {
-  return dicp::nn_argmin_impl<float>(q, tgt, N, n, m, S, idx_out, d2_out, ws, ws_bytes, stream);
+int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, int m, int S, const int32_t* m_valid, int32_t* idx_out,
+                       float* d2_out, void* ws, size_t ws_bytes, void* stream) {
+  return dicp::nn_argmin_impl<float>(q, tgt, N, n, m, S, m_valid, idx_out, d2_out, ws, ws_bytes, stream);
 }
-int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, int S, int32_t* idx_out, double* d2_out,
-                       void* ws, size_t ws_bytes, void* stream) {
-  return dicp::nn_argmin_impl<double>(q, tgt, N, n, m, S, idx_out, d2_out, ws, ws_bytes, stream);
+int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, int S, const int32_t* m_valid, int32_t* idx_out,
+                       double* d2_out, void* ws, size_t ws_bytes, void* stream) {
+  return dicp::nn_argmin_impl<double>(q, tgt, N, n, m, S, m_valid, idx_out, d2_out, ws, ws_bytes, stream);
 }
 size_t dicp_nn_packed_bytes(int N, int m, int elem_size) { return dicp::nn_packed_bytes(N, m, elem_size); }
-int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream) {
+int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, const int32_t* m_valid, void* packed, void* stream) {
   DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
-  return dicp::nn_pack_targets<float>(tgt, N, m, S, nullptr, (float4*)packed, (cudaStream_t)stream);
+  return dicp::nn_pack_targets<float>(tgt, N, m, S, m_valid, (float4*)packed, (cudaStream_t)stream);
 }
-int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void* stream) {
+int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, const int32_t* m_valid, void* packed, void* stream) {
   DICP_CHECK_ARG(tgt && packed && N >= 1 && N <= 65535 && m >= 1 && (S == 3 || S == 6), "bad arguments");
-  return dicp::nn_pack_targets<double>(tgt, N, m, S, nullptr, (double4*)packed, (cudaStream_t)stream);
+  return dicp::nn_pack_targets<double>(tgt, N, m, S, m_valid, (double4*)packed, (cudaStream_t)stream);
 }
 int dicp_nn_scan_f32(const float* q, const double* state, const void* packed, int N, int n, int m, int32_t* idx_out, float* d2_out,
                      void* ws, size_t ws_bytes, void* stream) {

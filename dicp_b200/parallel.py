@@ -167,7 +167,7 @@ class SplitTargetSearch:
         part = target[:, lo:hi, :3].contiguous()
         ml = hi - lo
         packed = torch.empty(lib.dicp_nn_packed_bytes(N, ml, source.element_size()), dtype=torch.uint8, device=dev)
-        _lib.check(getattr(lib, "dicp_nn_pack_" + sfx)(_lib.ptr(part), N, ml, 3, _lib.ptr(packed), st), "dicp_nn_pack")
+        _lib.check(getattr(lib, "dicp_nn_pack_" + sfx)(_lib.ptr(part), N, ml, 3, None, _lib.ptr(packed), st), "dicp_nn_pack")
         ws = _workspace(lib.dicp_nn_workspace_bytes(N, n, ml, source.element_size()), dev)
         idx_l = torch.empty((N, n), dtype=torch.int32, device=dev)
         d2_l = torch.empty((N, n), dtype=dt, device=dev)

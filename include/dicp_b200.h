@@ -82,6 +82,8 @@ DICP_API const char* dicp_last_error(void);
 /* ---- nearest neighbour: replaces cdist + argmin at dICP/nn.py:32-35 (== 83-86) --------
  * q   [N,n,3]   queries
  * tgt [N,m,S]   targets, S in {3,6}; only the first 3 columns are used
+ * m_valid [N]   int32 or NULL: number of real rows of every target cloud; rows beyond it (the padding
+ *               of a ragged batch) are never returned, whatever they contain
  * idx_out [N,n] int32 index of the nearest target (first minimum on exact ties)
  * d2_out  [N,n] squared distance to it, or NULL
  * The result is the argmin of the direct-form distance (x-y)^2 evaluated in the element type
@@ -89,17 +91,17 @@ DICP_API const char* dicp_last_error(void);
  * rescanned exactly), so it equals the exact-arithmetic argmin whenever the relative gap
  * between the two smallest squared distances exceeds a few ulp.                          */
 DICP_API size_t dicp_nn_workspace_bytes(int N, int n, int m, int elem_size);
-DICP_API int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, int m, int S,
+DICP_API int dicp_nn_argmin_f32(const float* q, const float* tgt, int N, int n, int m, int S, const int32_t* m_valid,
                        int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
-DICP_API int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, int S,
+DICP_API int dicp_nn_argmin_f64(const double* q, const double* tgt, int N, int n, int m, int S, const int32_t* m_valid,
                        int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
 
 /* Same result through a uniform grid: build (bounding box, counting sort)
  * + one-thread-per-query ring search.  ws sized by dicp_nn_grid_workspace_bytes.             */
 DICP_API size_t dicp_nn_grid_workspace_bytes(int N, int n, int m, int elem_size);
-DICP_API int dicp_nn_argmin_grid_f32(const float* q, const float* tgt, int N, int n, int m, int S,
+DICP_API int dicp_nn_argmin_grid_f32(const float* q, const float* tgt, int N, int n, int m, int S, const int32_t* m_valid,
                             int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
-DICP_API int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, int n, int m, int S,
+DICP_API int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, int n, int m, int S, const int32_t* m_valid,
                             int32_t* idx_out, double* d2_out, void* ws, size_t ws_bytes, void* stream);
 
 /* The two stages of dicp_nn_argmin_*, exported for profiling and for callers that search the
@@ -112,8 +114,8 @@ DICP_API int dicp_nn_argmin_grid_f64(const double* q, const double* tgt, int N, 
  * be NULL) receives the direct-form squared distance of the returned neighbour.  `ws` for the
  * scan is sized by dicp_nn_workspace_bytes.                                                  */
 DICP_API size_t dicp_nn_packed_bytes(int N, int m, int elem_size);
-DICP_API int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, void* packed, void* stream);
-DICP_API int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, void* packed, void* stream);
+DICP_API int dicp_nn_pack_f32(const float* tgt, int N, int m, int S, const int32_t* m_valid, void* packed, void* stream);
+DICP_API int dicp_nn_pack_f64(const double* tgt, int N, int m, int S, const int32_t* m_valid, void* packed, void* stream);
 DICP_API int dicp_nn_scan_f32(const float* q, const double* state, const void* packed, int N, int n, int m,
                      int32_t* idx_out, float* d2_out, void* ws, size_t ws_bytes, void* stream);
 DICP_API int dicp_nn_scan_f64(const double* q, const double* state, const void* packed, int N, int n, int m,

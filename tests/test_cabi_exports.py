@@ -34,7 +34,7 @@ def test_version_and_arg_errors():
     assert lib.dicp_icp_workspace_bytes(256, 16384, 16384, 4) > 0
     assert lib.dicp_nn_workspace_bytes(1, 1, 1, 4) > 0
     # null pointers / bad sizes are rejected before any CUDA call
-    rc = lib.dicp_nn_argmin_f32(None, None, 1, 1, 1, 3, None, None, None, 0, None)
+    rc = lib.dicp_nn_argmin_f32(None, None, 1, 1, 1, 3, None, None, None, None, 0, None)
     assert rc == -1 and b"null pointer" in lib.dicp_last_error()
     p = _lib.DicpParams()
     rc = lib.dicp_icp_forward_f32(None, None, None, None, None, 1, 1, 1, 6, ctypes.byref(p), None, None, None, None, None, None, None,

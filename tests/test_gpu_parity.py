@@ -203,6 +203,27 @@ def test_nn_far_from_origin_uses_exact_fallback(offset, extent):
     _nn_check(x.float(), y.float(), min_ok=0.95)
 
 
+@pytest.mark.parametrize("search", ["brute", "grid"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_nn_argmin_valid_counts_exclude_padding_rows(search, dtype):
+    """dicp_nn_argmin_*(…, m_valid, …) (SURVEY.md §8 b / f-1): rows beyond m_valid[b] are never returned, even when
+    they coincide with a query; the answer equals the search over the truncated cloud."""
+    from dicp_b200._functions import nn_argmin
+    gen = torch.Generator().manual_seed(21)
+    N, n, m = 3, 700, 450
+    y = (torch.rand((N, m, 3), generator=gen, dtype=torch.float64) * 10 - 5).to(dtype)
+    x = (torch.rand((N, n, 3), generator=gen, dtype=torch.float64) * 10 - 5).to(dtype)
+    valid = [450, 133, 32]
+    for b, mv in enumerate(valid):
+        y[b, mv:] = x[b, : m - mv]                            # poison: the padding rows are exact copies of queries
+    mvt = torch.tensor(valid, dtype=torch.int32, device="cuda")
+    idx, d2 = nn_argmin(x.cuda(), y.cuda(), return_d2=True, search=search, m_valid=mvt)
+    for b, mv in enumerate(valid):
+        ref_i, ref_d = nn_argmin(x[b:b + 1].cuda(), y[b:b + 1, :mv].contiguous().cuda(), return_d2=True, search="brute")
+        assert int(idx[b].max()) < mv
+        assert torch.equal(idx[b], ref_i[0]) and torch.equal(d2[b], ref_d[0])
+
+
 def test_nn_first_minimum_on_exact_ties():
     """duplicated targets: torch.argmin returns the first (nn.py:35)."""
     from dicp_b200._functions import nn_argmin

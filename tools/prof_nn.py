@@ -21,7 +21,7 @@ packed = torch.empty(lib.dicp_nn_packed_bytes(N, n, 4), dtype=torch.uint8, devic
 ws = torch.empty(max(lib.dicp_nn_workspace_bytes(N, n, n, 4), 256), dtype=torch.uint8, device=dev)
 idx = torch.empty((N, n), dtype=torch.int32, device=dev)
 st = _lib.stream_ptr(dev)
-_lib.check(lib.dicp_nn_pack_f32(_lib.ptr(tgt), N, n, 6, _lib.ptr(packed), st), "pack")
+_lib.check(lib.dicp_nn_pack_f32(_lib.ptr(tgt), N, n, 6, None, _lib.ptr(packed), st), "pack")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
 ev[0].record()
 for i in range(reps):
