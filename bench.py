@@ -111,20 +111,60 @@ def learning_loss(res, theta):
 
 
 # ---------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's torch-CPU path
+# reference arm / cpu baseline: the UNMODIFIED reference from baseline/_ref (baseline/install_ref.py),
+# driven through its own public API and stock code path (dICP/ICP.py:46-303, dICP/nn.py:11-40).
+# Only when baseline/_ref is absent: the oracle port of the same path, labelled kind "port".
 # ---------------------------------------------------------------------------------------
-def cpu_step(src, tgt):
-    from oracle.dicp_oracle import IcpSettings, icp_forward
-    cfg = IcpSettings(icp_type="pt2pl", max_iterations=ITERS, tolerance=1e-12, differentiable=True, const_iter=True,
-                      trim_dist=TRIM, loss_name=LOSS["name"], loss_metric=LOSS["metric"], dim=3)
-    n_pairs = src.shape[0]
-    s = src.clone().requires_grad_(True)
-    t = tgt.clone().requires_grad_(True)
-    T0 = torch.eye(4).repeat(n_pairs, 1, 1)
-    res = icp_forward(s, t, T0, torch.ones((n_pairs, NPTS)), cfg)
+def bench_config():
+    """The `config` object of the JSON line; identical in both arms."""
+    return {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "points": NPTS, "iterations": ITERS,
+            "l2": "inputs larger than L2 (source+target %.0f MB per GPU, plus 168 MB of saved correspondences "
+                  "written and re-read per step)" % (PAIRS_PER_GPU * NPTS * 9 * 4 / 1e6)}
+
+
+_CPU_ARM = {}
+
+
+def cpu_arm():
+    """-> (kind, step(src, tgt)) of the CPU implementation of the path: the reference itself, else the port."""
+    if _CPU_ARM:
+        return _CPU_ARM["kind"], _CPU_ARM["step"]
+    from baseline import ref_arm
+    ref = ref_arm.load_reference()
     theta = torch.arange(1, 13, dtype=torch.float32)
-    learning_loss(res, theta).backward()
-    return float(res["T"].sum())
+    if ref is not None:
+        cfg_path = ref_arm.reference_config(const_iter=True)
+        icp = ref.ICP(config_path=cfg_path, icp_type="pt2pl", max_iterations=ITERS, tolerance=1e-12, differentiable=True)
+
+        def step(src, tgt):
+            s = src.clone().requires_grad_(True)
+            t = tgt.clone().requires_grad_(True)
+            res = icp.icp(s, t, torch.eye(4).repeat(src.shape[0], 1, 1), trim_dist=TRIM, loss_fn=LOSS, dim=3)
+            learning_loss(res, theta).backward()
+            assert s.grad is not None and t.grad is not None and res["deltas"].shape[1] == ITERS
+            return float(res["T"].sum())
+        kind = "reference"
+    else:
+        from oracle.dicp_oracle import IcpSettings, icp_forward
+        cfg = IcpSettings(icp_type="pt2pl", max_iterations=ITERS, tolerance=1e-12, differentiable=True, const_iter=True,
+                          trim_dist=TRIM, loss_name=LOSS["name"], loss_metric=LOSS["metric"], dim=3)
+
+        def step(src, tgt):
+            s = src.clone().requires_grad_(True)
+            t = tgt.clone().requires_grad_(True)
+            res = icp_forward(s, t, torch.eye(4).repeat(src.shape[0], 1, 1), torch.ones(src.shape[:2]), cfg)
+            learning_loss(res, theta).backward()
+            return float(res["T"].sum())
+        kind = "port"
+    _CPU_ARM.update(kind=kind, step=step)
+    return kind, step
+
+
+CPU_ARM_DESCRIPTION = {
+    "reference": "unmodified utiasASRL/dICP from baseline/_ref: ICP(...).icp through its stock path (cdist + argmin + gather, "
+                 "bmm / linalg.inv / matrix_exp, torch autograd), const_iter via a copy of its own YAML",
+    "port": "baseline/_ref is absent: oracle port of dICP/ICP.py:132-303 (same torch CPU ops)",
+}
 
 
 def run_reference(args):
@@ -133,7 +173,8 @@ def run_reference(args):
         return
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    pairs_per_step = 1           # dense (n,m) distance matrix: 1.07 GB fp32 per pair
+    kind, cpu_step = cpu_arm()
+    pairs_per_step = 1           # dense (n,m) distance matrix: 1.07 GB fp32 per pair (the reference must be chunked over N)
     src, tgt = make_batch(pairs_per_step, 0)
     for _ in range(args.warmup):
         cpu_step(src, tgt)
@@ -147,10 +188,9 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_arm": "oracle port of dICP/ICP.py:132-303 (torch CPU ops cdist/argmin/gather/"
-                   "bmm/inv/matrix_exp + autograd); the unmodified reference is Python and is not present on the GPU box"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(),
+        "reference_arm": CPU_ARM_DESCRIPTION[kind],
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -237,7 +277,7 @@ def roofline_gn(src, tgt, idx, pk):
 
 def run_ours(args):
     import torch.distributed as dist
-    from dICP.ICP import ICP
+    from dicp_b200.ICP import ICP          # `dICP.ICP.ICP` of the drop-in alias package is this class
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -331,19 +371,21 @@ def run_ours(args):
             k: v for k, v in roofline_gn(src_d.detach().repeat(big, 1, 1), tgt_d.detach().repeat(big, 1, 1), idx.repeat(big, 1), pk).items()
             if k in ("achieved", "frac", "ms_per_launch", "units_per_launch")}
         cpu = None
-        if True:    # rank 0 times the CPU baseline at every N (a bounded sample: 8 x 1 pair, about 10 s)
+        if world == 1:    # rank 0 at N=1 only: a bounded sample (8 x 1 pair, 10-30 s of CPU work); at N>1 the ranks waiting
+            # in the barrier would starve it, and the driver's own reference arm covers those N
             cores = os.cpu_count()
             torch.set_num_threads(cores)
+            kind, cpu_step = cpu_arm()
             s1, t1 = src_h[:1].clone(), tgt_h[:1].clone()
             cpu_step(s1, t1)                        # warm-up (thread pool, allocator)
             t0 = time.perf_counter()
-            reps = 8                               # about 10 s of CPU work on the box's 16 cores
+            reps = 8
             for _ in range(reps):
                 cpu_step(s1, t1)
             cdt = time.perf_counter() - t0
-            cpu = {"value": reps / cdt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                   "sample": "%d x 1 pair of the C3 workload (fwd+bwd, 10 it), oracle port of the reference torch-CPU path, "
-                             "%d threads, %.1f s" % (reps, torch.get_num_threads(), cdt)}
+            cpu = {"value": reps / cdt, "unit": "pairs/s", "cores": cores, "kind": kind,
+                   "sample": "%d x 1 pair of the C3 workload (fwd+bwd, 10 it), %s, %d threads, %.1f s"
+                             % (reps, CPU_ARM_DESCRIPTION[kind], torch.get_num_threads(), cdt)}
         # kernels of libdicp_b200.so per step (profiles/r01_launches.md): forward init, bbox centres, NN pack, gather
         # records + 10 x (filter scan, exact fallback, unpack, GN accumulate, GN update) + finalize;
         # backward seed + 10 x (pair, points) + final pair
@@ -356,9 +398,8 @@ def run_ours(args):
             "metric": METRIC, "value": pairs_total * args.steps / sec, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_total": pairs_total, "l2": "inputs larger than L2 (source+target %.0f MB per GPU, "
-                       "plus 168 MB of saved correspondences written and re-read per step)" % ((src_h.numel() + tgt_h.numel()) * 4 / 1e6),
-                       "learning_mode_allreduce": "13 floats per step over NCCL" if world > 1 else "single GPU: no collective"},
+            "config": bench_config(), "pairs_total": pairs_total,
+            "learning_mode_allreduce": "13 floats per step over NCCL" if world > 1 else "single GPU: no collective",
             "clocks": clocks,
             "e2e": {"value": pairs_total * steps_e2e / sec_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * sec_e2e / steps_e2e, "api": "pinned host clouds -> H2D -> dICP.ICP.ICP.icp (forward) -> backward to the input points -> D2H of [loss, dloss/dtheta] and T"},

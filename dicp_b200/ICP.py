@@ -84,6 +84,11 @@ class ICP:
         # uniform grid built once per call (same correspondences, O(n) per iteration); optional YAML key
         # dICP.functionality.nn_search
         self.nn_search = func.get('nn_search', 'brute')
+        # not in the reference: when True, every call leaves the correspondences it used in
+        # `self.last_correspondences`, an int32 (K, N, n) CUDA tensor (iteration, pair, source point) -> target row.
+        # Parity tests replay them through the fp64 oracle (gradients are only comparable on equal correspondences)
+        self.keep_correspondences = False
+        self.last_correspondences = None
 
     def icp(self, source, target, T_init, weight=None, trim_dist=None, loss_fn=None, dim=3):
         return self.dICP(source, target, T_init, weight, trim_dist, loss_fn, dim)
@@ -151,9 +156,12 @@ class ICP:
         # pair split over the GPUs of a process group); it is bound to this call's clouds and then asked
         # for the correspondences of every iteration
         nn_hook = None if isinstance(self.nn_search, str) else self.nn_search.bind(source_d.detach(), target_d.detach(), m_valid)
+        keep = [] if self.keep_correspondences else None
         pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
             source_d, target_d, T_init.to(dev, non_blocking=True),
-            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook)
+            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook, keep)
+        if keep is not None:
+            self.last_correspondences = keep[0]
 
         if self.verbose:
             print("ICP converged in {} iterations".format(deltas.shape[1]))

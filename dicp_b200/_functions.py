@@ -194,7 +194,7 @@ class ICPFunction(torch.autograd.Function):
       (N, n) int32 tensor to fill, both views of this call's saved buffers, on the current stream."""
 
     @staticmethod
-    def forward(ctx, source, target, T_init, w_init, params, m_valid=None, nn_hook=None):
+    def forward(ctx, source, target, T_init, w_init, params, m_valid=None, nn_hook=None, keep_idx=None):
         require_cuda()
         lib = load_library()
         dev, dt = source.device, source.dtype
@@ -248,6 +248,8 @@ class ICPFunction(torch.autograd.Function):
         ctx.save_for_backward(source, target, w_init if w_init is not None else source.new_empty(0),
                               saved_idx, saved_state)
         ctx.ws = ws
+        if keep_idx is not None:                 # the caller asked for the correspondences (ICP.keep_correspondences)
+            keep_idx.append(saved_idx[:k_run])
         outs = (pc, T, deltas[:, :k_run], weights[:, :k_run], costs[:, :k_run], converged.bool(), num_iters, match_ratio)
         ctx.mark_non_differentiable(*outs[2:])
         return outs
@@ -272,4 +274,4 @@ class ICPFunction(torch.autograd.Function):
                 ptr(saved_idx), ptr(saved_state), ptr(g_T), ptr(g_pc), ptr(g_src), ptr(g_tgt), ptr(g_w), ptr(g_T0),
                 ptr(ws), ws.numel(), stream_ptr(dev))
         check(rc, "dicp_icp_backward_" + sfx)
-        return g_src, g_tgt, g_T0, g_w, None, None, None
+        return g_src, g_tgt, g_T0, g_w, None, None, None, None

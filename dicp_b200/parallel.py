@@ -156,6 +156,8 @@ class SplitTargetSearch:
         if m_valid is not None:
             raise ValueError("SplitTargetSearch does not take ragged (padded) target batches")
         lib = _lib.load_library()
+        # the scan reads dense (N,n,3) rows: ICP.dICP hands over the `source[:, :, :3]` view of a 6-column cloud
+        source = source.contiguous()
         N, n, _ = source.shape
         m = target.shape[1]
         lo, hi = shard_range(m, self.rank, self.world_size)
@@ -208,5 +210,5 @@ class SplitTargetSearch:
                 _lib.check(lib.dicp_nn_unpack_keys_f32(_lib.ptr(keys[j * count:]), count, _lib.ptr(idx_k), None, stream),
                            "dicp_nn_unpack_keys")
         hook.local = local
-        hook.keepalive = (part, packed, ws)
+        hook.keepalive = (source, part, packed, ws)
         return hook
