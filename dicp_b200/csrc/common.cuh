@@ -102,6 +102,26 @@ __device__ __forceinline__ void load_packed_row(const void* __restrict__ rows, s
     }
   }   // fp64 has no table: callers gather from the caller's rows (load_target_row)
 }
+// gather of one 24-byte fp32 target row (x,y,z,nx,ny,nz) from the caller's [.,6] tensor (16-byte aligned base, so a
+// row starts at a multiple of 8 bytes): the two aligned 16-byte loads that cover the 32-byte window holding the
+// row, then a select on the row's parity.  Against the 32-byte re-laid table this saves a quarter of the gather's
+// DRAM traffic (the whole 24 B/row tensor is fetched once; the table is 32 B/row) and the table itself.
+// `tensor_end`: the row is the last one of the whole tensor and the window would reach past it.
+__device__ __forceinline__ void load_row24(const float* __restrict__ row, bool tensor_end, float* q, float* nr) {
+  const bool odd = (reinterpret_cast<uintptr_t>(row) & 8) != 0;
+  if (tensor_end && !odd) {                     // rare: plain 8-byte loads
+    const float2 a = __ldg(reinterpret_cast<const float2*>(row)), b = __ldg(reinterpret_cast<const float2*>(row + 2)),
+                 c = __ldg(reinterpret_cast<const float2*>(row + 4));
+    q[0] = a.x; q[1] = a.y; q[2] = b.x; nr[0] = b.y; nr[1] = c.x; nr[2] = c.y;
+    return;
+  }
+  const float4* w = reinterpret_cast<const float4*>(reinterpret_cast<uintptr_t>(row) & ~(uintptr_t)15);
+  float4 v0, v1;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "l"(w));
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "l"(w + 1));
+  q[0] = odd ? v0.z : v0.x; q[1] = odd ? v0.w : v0.y; q[2] = odd ? v1.x : v0.z;
+  nr[0] = odd ? v1.y : v0.w; nr[1] = odd ? v1.z : v1.x; nr[2] = odd ? v1.w : v1.y;
+}
 // scatter-add of one 6-column gradient row: fp32 uses the 8-byte vector reduction (red.global.add.v2.f32)
 __device__ __forceinline__ void atomic_add_row6(float* row, const float* v) {
   atomicAdd(reinterpret_cast<float2*>(row), make_float2(v[0], v[1]));
@@ -170,7 +190,7 @@ int grid_search(const T* q, const double* state, int N, int n, int m, const Grid
                 const int* stop_flag, cudaStream_t st);
 
 // ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------
-int gn_blocks_per_pair(int n);
+int gn_blocks_per_pair(int N, int n);   // partial-sum rows per pair of the accumulate kernel's tile plan (tile_stream.cuh)
 int bw_blocks_per_pair(int n);
 // where the accumulate kernel finds (C, r, active) of pair b: state + b * stride + {c, r, active}
 // (active < 0: every pair is active).  The loop passes its saved-state records, the stage API a bare [N,12].

@@ -16,6 +16,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "tile_stream.cuh"
 
 namespace dicp {
 
@@ -27,161 +28,398 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int GN_THREADS = 128;
-#ifndef GN_PTS
-#define GN_PTS 16
+#ifndef GN_NT
+#define GN_NT 128
 #endif
-constexpr int GN_PTS_PER_THREAD = GN_PTS;  // 8 pipelined passes of 2: amortises the 31-value block reduction
-
-int bw_blocks_per_pair(int n) {          // backward point pass: 8 correspondences per thread (2 passes of 4)
-  int nb = (n + GN_THREADS * 8 - 1) / (GN_THREADS * 8);
-  if (nb < 1) nb = 1;
-  if (nb > 128) nb = 128;
-  return nb;
-}
-
-int gn_blocks_per_pair(int n) {
-  int nb = (n + GN_THREADS * GN_PTS_PER_THREAD - 1) / (GN_THREADS * GN_PTS_PER_THREAD);
-  if (nb < 1) nb = 1;
-  if (nb > 128) nb = 128;
-  return nb;
-}
-
-// block-wide sum of NV per-thread values: warp shuffle tree in the compute type (32 partials of
-// a handful of terms each), then double across warps; result lands in out[0..NV) of the CTA's
-// partial row.  Fixed tree => deterministic for a given launch shape.
-template <typename T, int NV>
-__device__ __forceinline__ void block_reduce_store(const T* vals, double* out, double* smem /* [warps][NV] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    T x = vals[v];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) smem[warp * NV + v] = (double)x;
-  }
-  __syncthreads();
-  if (threadIdx.x < NV) {
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += smem[w * NV + threadIdx.x];
-    out[threadIdx.x] = s;
-  }
-}
-
-template <typename T> struct GnUnroll;
+constexpr int GN_THREADS = GN_NT;
+#ifndef GN_ROWS24
+#define GN_ROWS24 0       // 1: point-to-plane gathers the caller's 24-byte rows directly (two aligned 16-byte loads) instead of the 32-byte
+                          // table: 15 % less DRAM traffic (184 vs 215 MB read at C3) but 1.5 sectors per row through L2: 71 vs 53 us, rejected
+#endif
 #ifndef GN_U
 #define GN_U 2
 #endif
-template <> struct GnUnroll<float> { static constexpr int U = GN_U; };   // correspondences per thread and pipeline stage
-template <> struct GnUnroll<double> { static constexpr int U = 1; };
-
+#ifndef GN_STAGES
+#define GN_STAGES 4
+#endif
 #ifndef GN_MINB
 #define GN_MINB 4
 #endif
+constexpr int GN_TILE = GN_THREADS * GN_U;      // correspondences per tile (one staged pass of the CTA)
+constexpr int GN_CTAS_PER_SM = GN_MINB;         // persistent CTAs per SM (the launch bounds guarantee the registers)
 
-template <typename T, bool PT2PL, int DIM, bool FASTW>
-__global__ void __launch_bounds__(GN_THREADS, sizeof(T) == 4 ? GN_MINB : 1)
-gn_accum_kernel(const T* __restrict__ source, const T* __restrict__ target, const void* __restrict__ rows,
-                const T* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, int S,
-                WeightParams P, T* __restrict__ weights_out, long long w_pair_stride,
-                double* __restrict__ partials, const int* __restrict__ stop_flag) {
-  if (stop_flag != nullptr && *stop_flag != 0) return;
-  __shared__ double red_smem[(GN_THREADS / 32) * RED_N];
-  constexpr int U = GnUnroll<T>::U;
-  const int b = blockIdx.y;
-  const double* rec = state.base + (size_t)b * state.stride;
-  T C[9], r[3];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) C[i] = (T)rec[state.c + i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) r[i] = (T)rec[state.r + i];
-  const T active = state.active >= 0 ? (T)rec[state.active] : T(1);
+int device_sm_count() {
+  static int cached = 0;                        // benign race: every thread computes the same value
+  if (cached == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) {
+      cudaGetLastError();
+      sms = 148;
+    }
+    cached = sms;
+  }
+  return cached;
+}
 
-  T acc[RED_N];
+#ifndef GN_K
+#define GN_K 8
+#endif
+TilePlan gn_tile_plan(int N, int n) { return make_tile_plan(N, n, GN_TILE, GN_CTAS_PER_SM, GN_K); }
+int gn_blocks_per_pair(int N, int n) { return gn_tile_plan(N, n).rows; }
+
+int bw_blocks_per_pair(int n) {          // backward point pass: 8 correspondences per thread (2 passes of 4)
+  int nb = (n + 1023) / 1024;
+  if (nb < 1) nb = 1;
+  if (nb > 128) nb = 128;
+  return nb;
+}
+
+// block-wide sum of NV (<= 32) per-thread values: per warp a 31-shuffle multi-value reduction in the compute type
+// (tile_stream.cuh), then double across warps; result lands in out[0..NV) of the segment's partial row.
+// Fixed tree => deterministic for a given launch shape.
+template <typename T, int NV>
+__device__ __forceinline__ void block_reduce_store(const T* vals, double* out, double* smem /* [warps][32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  T v[32];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = vals[i];
+  warp_multi_reduce<T, NV>(v);
+  smem[warp * 32 + lane] = (double)v[0];
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += smem[w * 32 + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();                               // smem is reused by the next segment this CTA reduces
+}
+
+// What a persistent CTA keeps per (chunk, pair) segment it is working on, and the hand-over between segments: the
+// partial sums go to the row of the pair's RED_N-wide table that the plan assigns to the segment (the number of
+// chunk boundaries between the start of the pair and the start of the segment); the segment that ends the pair also
+// clears the rows nobody writes, so that the update kernel can sum all plan.rows rows in index order.
+template <typename T>
+struct GnPairCtx {
+  T C[9], r[3], active;
+  int b;
+  long long seg_tile;     // first tile of the segment
+};
+template <typename T>
+__device__ __forceinline__ void gn_flush_segment(const TilePlan& plan, int b, long long seg_tile, long long last_tile, const T* acc,
+                                                 double* __restrict__ partials, double* red_smem) {
+  const long long pair_tile = (long long)b * plan.tpp;
+  const int row = tp_segment_row(plan, b, seg_tile);
+  double* rows_b = partials + (size_t)b * plan.rows * RED_N;
+  block_reduce_store<T, RED_N>(acc, rows_b + (size_t)row * RED_N, red_smem);
+  if (last_tile == pair_tile + plan.tpp - 1) {
+    for (int i = (row + 1) * RED_N + threadIdx.x; i < plan.rows * RED_N; i += blockDim.x) rows_b[i] = 0.0;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void gn_enter_segment(GnPairCtx<T>& ctx, int b, long long seg_tile, const StateView& state, T* acc) {
+  if (b != ctx.b) {
+    const double* rec = state.base + (size_t)b * state.stride;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ctx.C[i] = (T)rec[state.c + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ctx.r[i] = (T)rec[state.r + i];
+    ctx.active = state.active >= 0 ? (T)rec[state.active] : T(1);
+    ctx.b = b;
+  }
+  ctx.seg_tile = seg_tile;
 #pragma unroll
   for (int i = 0; i < RED_N; ++i) acc[i] = T(0);
+}
 
-  const T* src_b = source + (size_t)b * n * 3;
-  const T* tgt_b = target + (size_t)b * m * S;
-  const size_t row_b = (size_t)b * m;
-  const bool packed = sizeof(T) == 4 && rows != nullptr;
-  const int32_t* idx_b = idx + (size_t)b * n;
-  constexpr int R = PT2PL ? 1 : 3;
-  T* wout = weights_out != nullptr ? weights_out + (size_t)b * w_pair_stride : nullptr;
-
-  // Three-stage software pipeline in registers, U correspondences per thread and stage: while pass t
-  // is evaluated, the row gathers of pass t+1 and the index / point / weight loads of pass t+2 are in
-  // flight (the gather address depends on the index, so one stage cannot cover both latencies).
-  // Without it a warp alternates between waiting for HBM and computing, and with 16 warps per SM
-  // (the 31 accumulators cost the registers) nothing else fills the gaps.
-  struct StageA { int ii[U], jj[U]; T p[U][3], w0[U]; };
-  struct StageB { T q[U][3], nr[U][3]; };
-  auto load_a = [&](StageA& a, int base) {
+// ---------------------------------------------------------------------------------------------------------
+// fp32 fast path: streams staged in shared memory by TMA bulk copies, target rows gathered one tile ahead.
+// Requirements (checked by the launcher): n % 4 == 0 and 16-byte aligned source / idx / w_init, so that every
+// slice of each stream starts on a 16-byte boundary and has a 16-byte multiple length; `rows` built.
+//
+// The CTA's ring has STAGES stages of { idx[TILE] | p[3 TILE] | w0[TILE] } with a "full" mbarrier (bulk-copy
+// transaction bytes) and an "empty" mbarrier (one arrival per warp) per stage.  No __syncthreads separates
+// tiles: every warp waits for a stage on its own, releases it on its own, and the warp whose turn it is (tile L
+// is fed by warp L % WARPS) refills the stage that was released one step earlier, so the warps of a CTA drift by up
+// to a tile and their memory waits and arithmetic interleave instead of lining up (12 loosely coupled streams
+// per SM instead of 3 lock-stepped CTAs).  Lane l of warp w owns correspondences [U (32 w + l), +U) of the tile:
+// its indices / prior weights are one LDS.128, its points three, its weights row one STG.128.  The (C, r, active)
+// record of the next segment's pair is fetched one step ahead with cp.async into a per-warp slot.
+// ---------------------------------------------------------------------------------------------------------
+template <bool PT2PL, int DIM, bool FASTW>
+__global__ void __launch_bounds__(GN_THREADS, GN_MINB)
+gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict__ target, const void* __restrict__ rows,
+                       const float* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, WeightParams P,
+                       float* __restrict__ weights_out, long long w_pair_stride, double* __restrict__ partials, TilePlan plan,
+                       const int* __restrict__ stop_flag, int N) {
+  if (stop_flag != nullptr && *stop_flag != 0) return;
+  constexpr int U = GN_U, TILE = GN_TILE, STAGES = GN_STAGES, R = PT2PL ? 1 : 3, WARPS = GN_THREADS / 32;
+  static_assert(STAGES >= 3, "a stage is refilled one step after its release");
+  // dynamic shared memory: STAGES x { idx[TILE] | p[3 TILE] | w0[TILE] } (20 TILE bytes), reduction scratch, state slots, barriers
+  extern __shared__ __align__(128) unsigned char gn_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto st_idx = [&](int s) { return reinterpret_cast<int32_t*>(gn_smem + (size_t)s * TILE * 20); };
+  auto st_p = [&](int s) { return reinterpret_cast<float*>(gn_smem + (size_t)s * TILE * 20 + TILE * 4); };
+  auto st_w = [&](int s) { return reinterpret_cast<float*>(gn_smem + (size_t)s * TILE * 20 + TILE * 16); };
+  double* red_smem = reinterpret_cast<double*>(gn_smem + (size_t)STAGES * TILE * 20);
+  double* slot = red_smem + WARPS * 32 + warp * 16;            // this warp's (C, r, active) record of the next segment
+  uint64_t* full = reinterpret_cast<uint64_t*>(red_smem + WARPS * 32 + WARPS * 16);
+  uint64_t* empty = full + STAGES;
+  TileWalk walk;
+  walk.init(plan, blockIdx.x);
+  const int ntiles = walk.ntiles;
+  if (ntiles == 0) return;
+  if (tid == 0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * GN_THREADS + threadIdx.x;
-      a.ii[u] = i < n ? i : -1;
-      const int ic = i < n ? i : n - 1;
-      a.jj[u] = idx_b[ic];
-      a.p[u][0] = src_b[3 * ic]; a.p[u][1] = src_b[3 * ic + 1]; a.p[u][2] = src_b[3 * ic + 2];
-      a.w0[u] = (w_init != nullptr ? w_init[(size_t)b * n + ic] : T(1)) * active;          // ICP.py:257
-    }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // Tile L of this CTA lives in ring stage L % STAGES, use number L / STAGES of that stage.
+  typedef TileCursor Cursor;
+  auto tile_count = [&](const Cursor& c) { return min(TILE, n - c.j * TILE); };
+
+  // one lane feeds the ring
+  auto issue = [&](const Cursor& c) {
+    const int s = c.L % STAGES;
+    const int i0 = c.j * TILE;
+    const uint32_t cnt = (uint32_t)tile_count(c);
+    const size_t o = (size_t)c.b * n + i0;
+    mbar_expect_tx(&full[s], cnt * (w_init != nullptr ? 20u : 16u));
+    bulk_g2s(st_idx(s), idx + o, cnt * 4u, &full[s]);
+    bulk_g2s(st_p(s), source + o * 3, cnt * 12u, &full[s]);
+    if (w_init != nullptr) bulk_g2s(st_w(s), w_init + o, cnt * 4u, &full[s]);
   };
-  auto load_b = [&](StageB& g, const StageA& a) {
-    if (packed) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) load_packed_row<T, PT2PL>(rows, row_b + a.jj[u], g.q[u], g.nr[u]);
+  // asynchronous fetch of a pair's (C, r, active) doubles into the warp's slot
+  auto prefetch_state = [&](int b) {
+    const double* rec = state.base + (size_t)b * state.stride;
+    if (lane < 12) cp_async8(slot + lane, rec + (lane < 9 ? state.c + lane : state.r + lane - 9));
+    else if (lane == 12 && state.active >= 0) cp_async8(slot + 12, rec + state.active);
+  };
+
+  struct Gathered { float q[U][3], nr[U][3]; };
+  // waits for the tile's streams, then issues the row gathers of this lane's U correspondences
+  auto gather = [&](const Cursor& c, Gathered& g) {
+    const int s = c.L % STAGES;
+    const int cnt = tile_count(c);
+    mbar_wait(&full[s], (uint32_t)((c.L / STAGES) & 1));
+    const size_t row_b = (size_t)c.b * m;
+    const bool last_pair = c.b == N - 1;                       // the very last row of the tensor must not be over-read
+    int jj[U];
+    if (U == 4) {
+      const int4 v = *reinterpret_cast<const int4*>(st_idx(s) + tid * U);
+      jj[0] = v.x; jj[1 % U] = v.y; jj[2 % U] = v.z; jj[3 % U] = v.w;
     } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) load_target_row<T, PT2PL>(tgt_b + (size_t)a.jj[u] * S, S, g.q[u], g.nr[u]);
+      for (int u = 0; u < U; ++u) jj[u] = st_idx(s)[tid * U + u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = tid * U + u < cnt ? jj[u] : 0;           // lanes past the end of the cloud gather row 0 and are masked below
+      if (PT2PL && GN_ROWS24) load_row24(target + (row_b + j) * 6, last_pair && j == m - 1, g.q[u], g.nr[u]);
+      else load_packed_row<float, PT2PL>(rows, row_b + j, g.q[u], g.nr[u]);
     }
   };
-  // one pipeline step: loads of pass t+2 into `an2`, gathers of pass t+1 (an1 -> gn1), arithmetic of pass t (ac, gc)
-  auto step = [&](const StageA& ac, const StageB& gc, const StageA& an1, StageB& gn1, StageA& an2, int base, int stride) {
-    load_a(an2, base + 2 * stride);
-    load_b(gn1, an1);
-    // branch-free over the U correspondences so that their long dependent chains (sqrt, tanh, div)
-    // interleave; lanes past the end of the cloud evaluate a clamped copy and are masked out
-    PointEval<T> s[U];
+
+  float acc[RED_N];
+  GnPairCtx<float> ctx;
+  ctx.b = -1;
+  long long last_tile = 0;
+  struct Staged { float p[U][3], w0[U]; };
+  // this lane's points and prior weights of the tile, from the ring
+  auto read_stage = [&](const Cursor& c, Staged& in) {
+    const int s = c.L % STAGES;
+    const float4* sp = reinterpret_cast<const float4*>(st_p(s) + tid * U * 3);
+    float flat[U * 3];
+    if (U == 4) {
+      const float4 a = sp[0], bq = sp[1], cq = sp[2];
+      flat[0] = a.x; flat[1] = a.y; flat[2] = a.z; flat[3] = a.w;
+      flat[4 % (U * 3)] = bq.x; flat[5 % (U * 3)] = bq.y; flat[6 % (U * 3)] = bq.z; flat[7 % (U * 3)] = bq.w;
+      flat[8 % (U * 3)] = cq.x; flat[9 % (U * 3)] = cq.y; flat[10 % (U * 3)] = cq.z; flat[11 % (U * 3)] = cq.w;
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u) eval_point<T, PT2PL, FASTW>(C, r, ac.p[u], gc.q[u], gc.nr[u], ac.w0[u], P, s[u]);
-    if (base + GN_THREADS * U <= n) {
+      for (int k = 0; k < U * 3; ++k) flat[k] = st_p(s)[tid * U * 3 + k];
+    }
 #pragma unroll
-      for (int u = 0; u < U; ++u) accum_point<T, PT2PL, DIM>(acc, s[u], ac.w0[u], (T)P.thresh);
+    for (int u = 0; u < U; ++u) { in.p[u][0] = flat[3 * u]; in.p[u][1] = flat[3 * u + 1]; in.p[u][2] = flat[3 * u + 2]; }
+    if (w_init != nullptr) {
+      if (U == 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(st_w(s) + tid * U);
+        in.w0[0] = w4.x; in.w0[1 % U] = w4.y; in.w0[2 % U] = w4.z; in.w0[3 % U] = w4.w;
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) in.w0[u] = st_w(s)[tid * U + u];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) in.w0[u] = 1.0f;
+    }
+  };
+  auto compute = [&](const Cursor& c, const Gathered& g, Staged& in) {
+    const int b = c.b;
+    const int i0 = c.j * TILE;
+    const int cnt = tile_count(c);
+#pragma unroll
+    for (int u = 0; u < U; ++u) in.w0[u] *= ctx.active;                                           // ICP.py:257
+    PointEval<float> ev[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) eval_point<float, PT2PL, FASTW>(ctx.C, ctx.r, in.p[u], g.q[u], g.nr[u], in.w0[u], P, ev[u]);
+    if (cnt == TILE) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) accum_point<float, PT2PL, DIM>(acc, ev[u], in.w0[u], (float)P.thresh);
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (ac.ii[u] >= 0) accum_point<T, PT2PL, DIM>(acc, s[u], ac.w0[u], (T)P.thresh);
+        if (tid * U + u < cnt) accum_point<float, PT2PL, DIM>(acc, ev[u], in.w0[u], (float)P.thresh);
     }
-    if (wout != nullptr) {
+    if (weights_out != nullptr) {                                                                 // ICP.py:222, 164-165
+      float* wrow = weights_out + (size_t)b * w_pair_stride + (size_t)(i0 + tid * U) * R;
+      if (U == 4 && cnt == TILE && (reinterpret_cast<uintptr_t>(wrow) & 15) == 0) {
+        if (R == 1) {
+          __stcs(reinterpret_cast<float4*>(wrow), make_float4(ev[0].w, ev[1 % U].w, ev[2 % U].w, ev[3 % U].w));
+        } else {
+          __stcs(reinterpret_cast<float4*>(wrow), make_float4(ev[0].w, ev[0].w, ev[0].w, ev[1 % U].w));
+          __stcs(reinterpret_cast<float4*>(wrow) + 1, make_float4(ev[1 % U].w, ev[1 % U].w, ev[2 % U].w, ev[2 % U].w));
+          __stcs(reinterpret_cast<float4*>(wrow) + 2, make_float4(ev[2 % U].w, ev[3 % U].w, ev[3 % U].w, ev[3 % U].w));
+        }
+      } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (ac.ii[u] < 0) continue;
+        for (int u = 0; u < U; ++u) {
+          if (tid * U + u >= cnt) continue;
 #pragma unroll
-        for (int k = 0; k < R; ++k) wout[(size_t)ac.ii[u] * R + k] = s[u].w;                   // ICP.py:222, 164-165
+          for (int k = 0; k < R; ++k) wrow[u * R + k] = ev[u].w;
+        }
       }
     }
   };
-  const int stride = gridDim.x * (GN_THREADS * U);
-  int base = blockIdx.x * (GN_THREADS * U);
-  if (base < n) {
-    // the three stage buffers rotate by name over a loop unrolled by three: a register-to-register
-    // rotation at the end of each pass would wait for the loads it has just issued
-    StageA a0, a1, a2;
-    StageB g0, g1, g2;
-    load_a(a0, base);
-    load_a(a1, base + stride);
-    load_b(g0, a0);
-    for (;;) {
-      step(a0, g0, a1, g1, a2, base, stride);
-      if ((base += stride) >= n) break;
-      step(a1, g1, a2, g2, a0, base, stride);
-      if ((base += stride) >= n) break;
-      step(a2, g2, a0, g0, a1, base, stride);
-      if ((base += stride) >= n) break;
+  // start of a (chunk, pair) segment: hand over the sums of the previous one, take the pair's record from the slot
+  auto enter = [&](const Cursor& c) {
+    if (c.L > 0) gn_flush_segment<float>(plan, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
+    cp_async_wait_all();
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ctx.C[i] = (float)slot[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ctx.r[i] = (float)slot[9 + i];
+    ctx.active = state.active >= 0 ? (float)slot[12] : 1.0f;
+    ctx.b = c.b;
+    ctx.seg_tile = c.tile(plan);
+#pragma unroll
+    for (int i = 0; i < RED_N; ++i) acc[i] = 0.0f;
+    __syncwarp();                                              // the slot may be refilled from here on
+  };
+
+  Cursor ci, cg;                                  // next tile to feed into the ring / tile whose rows are being gathered
+  ci.init(plan, walk);
+  cg.init(plan, walk);
+  // one pipeline step: tile `cc` is computed with the rows gathered one step earlier (gc) while the rows of the next
+  // tile (cg -> gn) are requested; shared-memory reads of this tile go first so that they do not queue behind the gathers
+  auto step = [&](const Gathered& gc, Gathered& gn) {
+    const Cursor cc = cg;
+    if (cc.seg_first) enter(cc);                               // CTA-uniform: every warp walks the same tiles
+    last_tile = cc.tile(plan);
+    Staged in;
+    read_stage(cc, in);
+    cg.next(plan, walk);
+    if (cg.L < ntiles) {
+      if (cg.seg_first) prefetch_state(cg.b);
+      gather(cg, gn);
+    }
+    // this warp is done with the stage of tile cc (indices at gather time, points / weights just now)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[cc.L % STAGES]);
+    // the ring is fed one step behind the releases: tile ci goes into the stage of tile cc - 1, which every warp has
+    // normally left by now; the warps take turns as feeder
+    if (ci.L < ntiles) {
+      if (warp == (ci.L % WARPS) && lane == 0) {
+        if (ci.L >= STAGES) mbar_wait(&empty[ci.L % STAGES], (uint32_t)((ci.L / STAGES - 1) & 1));
+        issue(ci);
+      }
+      ci.next(plan, walk);
+    }
+    compute(cc, gc, in);
+  };
+
+  // prologue: the first tile alone, so that the first gathers do not queue behind the whole ring's worth of streams
+  if (tid == 0) issue(ci);
+  ci.next(plan, walk);
+  prefetch_state(cg.b);
+  Gathered ga, gb;
+  gather(cg, ga);
+  if (tid == 0) {
+    for (int s = 1; s < STAGES - 1 && ci.L < ntiles; ++s) { issue(ci); ci.next(plan, walk); }
+  }
+  ci.L = min(STAGES - 1, ntiles);                 // every thread's copy of the feeder cursor: re-walk to where lane 0 is
+  {
+    Cursor t;
+    t.init(plan, walk);
+    while (t.L < ci.L) t.next(plan, walk);
+    ci = t;
+  }
+  // the two gather buffers alternate by name over a loop unrolled by two (a register rotation would wait for the
+  // loads it has just issued)
+#pragma unroll 1
+  for (;;) {
+    step(ga, gb);
+    if (cg.L >= ntiles) break;
+    step(gb, ga);
+    if (cg.L >= ntiles) break;
+  }
+  gn_flush_segment<float>(plan, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic path (fp64, or fp32 inputs that do not meet the alignment rules of the staged kernel): the same tile
+// plan and partial-row layout, plain loads, one correspondence per thread and pass.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool PT2PL, int DIM, bool FASTW>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_accum_generic_kernel(const T* __restrict__ source, const T* __restrict__ target, const void* __restrict__ rows,
+                        const T* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, int S,
+                        WeightParams P, T* __restrict__ weights_out, long long w_pair_stride, double* __restrict__ partials,
+                        TilePlan plan, const int* __restrict__ stop_flag) {
+  if (stop_flag != nullptr && *stop_flag != 0) return;
+  __shared__ double red_smem[(GN_THREADS / 32) * 32];
+  constexpr int R = PT2PL ? 1 : 3;
+  TileWalk walk;
+  walk.init(plan, blockIdx.x);
+  const int ntiles = walk.ntiles;
+  if (ntiles == 0) return;
+  const bool packed = sizeof(T) == 4 && rows != nullptr;
+  T acc[RED_N];
+  GnPairCtx<T> ctx;
+  ctx.b = -1;
+  long long last_tile = 0;
+  TileCursor c;
+  for (c.init(plan, walk); c.L < ntiles; c.next(plan, walk)) {
+    const int b = c.b;
+    const int i0 = c.j * plan.tile;
+    if (c.seg_first) {
+      if (c.L > 0) gn_flush_segment<T>(plan, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
+      gn_enter_segment<T>(ctx, b, c.tile(plan), state, acc);
+    }
+    last_tile = c.tile(plan);
+    const T* src_b = source + (size_t)b * n * 3;
+    const int32_t* idx_b = idx + (size_t)b * n;
+    const int i_end = min(i0 + plan.tile, n);
+    for (int i = i0 + threadIdx.x; i < i_end; i += GN_THREADS) {
+      const int j = idx_b[i];
+      const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
+      const T w0 = (w_init != nullptr ? w_init[(size_t)b * n + i] : T(1)) * ctx.active;           // ICP.py:257
+      T q[3], nr[3];
+      if (packed) load_packed_row<T, PT2PL>(rows, (size_t)b * m + j, q, nr);
+      else load_target_row<T, PT2PL>(target + ((size_t)b * m + j) * S, S, q, nr);
+      PointEval<T> ev;
+      eval_point<T, PT2PL, FASTW>(ctx.C, ctx.r, p, q, nr, w0, P, ev);
+      accum_point<T, PT2PL, DIM>(acc, ev, w0, (T)P.thresh);
+      if (weights_out != nullptr) {
+        T* wrow = weights_out + (size_t)b * w_pair_stride + (size_t)i * R;
+#pragma unroll
+        for (int k = 0; k < R; ++k) wrow[k] = ev.w;                                               // ICP.py:222, 164-165
+      }
     }
   }
-  block_reduce_store<T, RED_N>(acc, partials + ((size_t)b * gridDim.x + blockIdx.x) * RED_N, red_smem);
+  gn_flush_segment<T>(plan, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
 }
 
 // ---- fp32 gather table ------------------------------------------------------------------
@@ -222,21 +460,54 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
                   int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,
                   double* partials, const int* stop_flag, cudaStream_t st) {
   const WeightParams P = make_weight_params(p);
-  dim3 grid(gn_blocks_per_pair(n), N);
+  const TilePlan plan = gn_tile_plan(N, n);
   const bool pl = p->icp_type == DICP_PT2PL;
   const bool fast = weight_params_fast(P);
-#define DICP_GN_LAUNCH(PL, DM)                                                                                                          \
-  do {                                                                                                                                  \
-    if (fast) gn_accum_kernel<T, PL, DM, true><<<grid, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P,        \
-                                                                            weights_out, w_pair_stride, partials, stop_flag);           \
-    else gn_accum_kernel<T, PL, DM, false><<<grid, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P,            \
-                                                                        weights_out, w_pair_stride, partials, stop_flag);               \
+  if (N > 65535) { set_error("gn_accumulate: N > 65535 pairs per call is not supported"); return DICP_ERR_ARG; }
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  // the staged kernel moves 16-byte aligned slices of the streams with bulk copies
+  const bool rows24 = GN_ROWS24 && pl && S == 6 && aligned16(target);      // see load_row24
+  const bool staged = sizeof(T) == 4 && (rows24 || rows != nullptr) && (n % 4) == 0 && aligned16(source) && aligned16(idx) && aligned16(w_init);
+  if (staged) {
+    if constexpr (sizeof(T) == 4) {
+      constexpr size_t smem = (size_t)GN_STAGES * GN_TILE * 20 + (GN_THREADS / 32) * (32 + 16) * sizeof(double) + 2 * GN_STAGES * sizeof(uint64_t);
+#define DICP_GN_LAUNCH1(PL, DM, FW)                                                                                                \
+  do {                                                                                                                             \
+    static bool attr_set = false;     /* idempotent: a race only repeats the call */                                               \
+    if (!attr_set) {                                                                                                               \
+      DICP_CUDA(cudaFuncSetAttribute(gn_accum_staged_kernel<PL, DM, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_set = true;                                                                                                             \
+    }                                                                                                                              \
+    gn_accum_staged_kernel<PL, DM, FW><<<dim3(plan.ctas, 1, 1), GN_THREADS, smem, st>>>(                                            \
+        source, target, (pl && rows24) ? nullptr : rows, w_init, idx, state, n, m, P, weights_out, w_pair_stride, partials, plan,  \
+        stop_flag, N);                                                                                                             \
   } while (0)
-  if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
-  else if (pl) DICP_GN_LAUNCH(true, 2);
-  else if (p->dim == 3) DICP_GN_LAUNCH(false, 3);
-  else DICP_GN_LAUNCH(false, 2);
+#define DICP_GN_LAUNCH(PL, DM)             \
+  do {                                     \
+    if (fast) DICP_GN_LAUNCH1(PL, DM, true); \
+    else DICP_GN_LAUNCH1(PL, DM, false);   \
+  } while (0)
+      if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
+      else if (pl) DICP_GN_LAUNCH(true, 2);
+      else if (p->dim == 3) DICP_GN_LAUNCH(false, 3);
+      else DICP_GN_LAUNCH(false, 2);
 #undef DICP_GN_LAUNCH
+#undef DICP_GN_LAUNCH1
+    }
+  } else {
+#define DICP_GN_LAUNCH(PL, DM)                                                                                                     \
+  do {                                                                                                                             \
+    if (fast) gn_accum_generic_kernel<T, PL, DM, true><<<plan.ctas, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P, \
+                                                                                       weights_out, w_pair_stride, partials, plan, stop_flag); \
+    else gn_accum_generic_kernel<T, PL, DM, false><<<plan.ctas, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P, \
+                                                                                   weights_out, w_pair_stride, partials, plan, stop_flag); \
+  } while (0)
+    if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
+    else if (pl) DICP_GN_LAUNCH(true, 2);
+    else if (p->dim == 3) DICP_GN_LAUNCH(false, 3);
+    else DICP_GN_LAUNCH(false, 2);
+#undef DICP_GN_LAUNCH
+  }
   DICP_LAUNCH_CHECK();
   return 0;
 }
@@ -367,7 +638,7 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
   w.packed = ar.take<char>(nn_packed_bytes(N, m, elem_size));
   w.nn_ws_bytes = nn_search_ws_bytes(N, n, m, elem_size);
   w.nn_ws = ar.take<char>(w.nn_ws_bytes > 0 ? w.nn_ws_bytes : 1);
-  w.partials = ar.take<double>((size_t)N * gn_blocks_per_pair(n) * RED_N);
+  w.partials = ar.take<double>((size_t)N * gn_blocks_per_pair(N, n) * RED_N);
   w.ctrl = ar.take<Ctrl>(1);
   w.bw_state = ar.take<double>((size_t)N * BW_STRIDE);
   w.bw_partials = ar.take<double>((size_t)N * bw_blocks_per_pair(n) * BW_NRED);
@@ -403,7 +674,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   const int K = p->max_iterations;
   const bool pl = p->icp_type == DICP_PT2PL;
   const long long nw = (long long)n * (pl ? 1 : 3);
-  const int nblk = gn_blocks_per_pair(n);
+  const int nblk = gn_blocks_per_pair(N, n);
   const int check_every = p->check_every >= 1 ? p->check_every : 1;
   const size_t rec_stride = (size_t)N * ST_STRIDE;
 
@@ -459,7 +730,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
       if (h.stop) break;
     }
   }
-  dim3 fgrid(gn_blocks_per_pair(n), N);
+  dim3 fgrid((n + 2047) / 2048 < 128 ? (n + 2047) / 2048 : 128, N);
   finalize_kernel<T><<<fgrid, 256, 0, st>>>(source, n, saved_state, N, w.ctrl, p->match_ratio_thresh, (double)nw,
                                             pc, T_out, num_iters, match_ratio);
   DICP_LAUNCH_CHECK();
@@ -575,7 +846,7 @@ int dicp_solve_update_f64(const double* partials, int nblk, const double* C_r, i
                           double* C_r_next, uint8_t* below_tolerance, void* stream) {
   return dicp::solve_update_api<double>(partials, nblk, C_r, N, params, delta, C_r_next, below_tolerance, stream);
 }
-int dicp_gn_blocks_per_pair(int n) { return dicp::gn_blocks_per_pair(n); }
+int dicp_gn_blocks_per_pair(int N, int n) { return N >= 1 && n >= 1 ? dicp::gn_blocks_per_pair(N, n) : 0; }
 size_t dicp_gn_rows_bytes(int N, int m, int elem_size) { return dicp::gn_rows_bytes(N, m, elem_size); }
 int dicp_gn_pack_rows_f32(const float* target, int N, int m, int S, int icp_type, void* rows, void* stream) {
   if (!target || !rows || N < 1 || m < 1 || (S != 3 && S != 6) || (icp_type == DICP_PT2PL && S != 6)) {

@@ -210,15 +210,16 @@ DICP_API int dicp_icp_backward_f64(const double* source, const double* target, c
 
 /* ---- single Gauss-Newton stage, exported for tests and profiling -------------------------
  * One iteration's accumulate (ICP.py:143-200) on given correspondences, exactly the kernel
- * launch of the loop.  partials_out [N, dicp_gn_blocks_per_pair(n), 32] doubles (31 used): one row per
- * CTA, which the loop's update kernel sums in index order; after the sum: upper-triangular A
+ * launch of the loop.  partials_out [N, dicp_gn_blocks_per_pair(N, n), 32] doubles (31 used): one row per
+ * persistent CTA that worked on the pair (unused rows are written as zeros), which the loop's update
+ * kernel sums in index order; after the sum: upper-triangular A
  * (21 | 6) at 0, b (6 | 3) at 21, cost at 27, sum(w) 28, #(w>thresh) 29, #(w_init>thresh) 30.
  * C_r [N,12] = row-major C then r, in double.
  * rows (fp32 only, may be NULL): the targets re-laid by dicp_gn_pack_rows_f32 as one aligned
  * record per row (32 B (x,y,z,nx,ny,nz,0,0) for pt2pl, 16 B (x,y,z,0) for pt2pt; N*m*32 bytes
  * reserved = dicp_gn_rows_bytes) so that a correspondence is one 256-/128-bit load; the
  * loop builds this table once per call.  NULL gathers from `target` directly.               */
-DICP_API int dicp_gn_blocks_per_pair(int n);
+DICP_API int dicp_gn_blocks_per_pair(int N, int n);
 DICP_API size_t dicp_gn_rows_bytes(int N, int m, int elem_size);
 DICP_API int dicp_gn_pack_rows_f32(const float* target, int N, int m, int S, int icp_type, void* rows, void* stream);
 DICP_API int dicp_gn_accumulate_f32(const float* source, const float* target, const void* rows, const float* w_init,

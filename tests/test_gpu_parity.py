@@ -356,7 +356,7 @@ def test_gn_accumulate_stage_vs_oracle():
         p = _functions.make_params("pt2pl", 3, True, "cauchy", 0.5, 2.0, 5.0, 1e-12, 1, True, 0.0)
         s_d, t_d = src.to(dt).cuda(), tgt.to(dt).cuda()
         C_r = torch.cat((torch.eye(3, dtype=torch.float64).reshape(1, 9).repeat(N, 1), torch.zeros((N, 3), dtype=torch.float64)), 1).cuda()
-        nblk = lib.dicp_gn_blocks_per_pair(n)
+        nblk = lib.dicp_gn_blocks_per_pair(N, n)
         wout = torch.empty((N, n), dtype=dt, device="cuda")
         st = _lib.stream_ptr(s_d.device)
         variants = [None]
@@ -376,7 +376,8 @@ def test_gn_accumulate_stage_vs_oracle():
             _lib.check(rc, "gn_accumulate")
             reds.append(part.sum(1))
         if len(reds) == 2:
-            assert torch.equal(reds[0], reds[1])      # same arithmetic, only the load path differs
+            # same per-point arithmetic; the staged kernel (aligned table, TMA-fed ring) and the generic one sum in a different order
+            assert torch.allclose(reds[0], reds[1], rtol=1e-5, atol=1e-5)
         red = reds[-1]
         red = red.cpu()
         A = torch.zeros((N, 6, 6), dtype=torch.float64)
