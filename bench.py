@@ -281,6 +281,46 @@ def roofline_gn(src, tgt, idx, pk):
             "units_per_launch": float(N) * n, "pairs": N}
 
 
+def roofline_bwd(src, tgt, pk, with_weight):
+    """Backward point pass (bwd_points_staged_kernel, HBM bound): the reverse loop of one ICP call is timed through the
+    C entry dicp_icp_backward_f32 at K = 10 and K = 5 saved iterations; the difference / 5 is one reverse iteration
+    (one bwd_pair_kernel + one bwd_points kernel launch), free of the once-per-call seed / table passes."""
+    from dicp_b200 import _functions, _lib
+    lib = _lib.load_library()
+    N, n, m = src.shape[0], src.shape[1], tgt.shape[1]
+    dev = src.device
+    p = _functions.make_params("pt2pl", 3, True, LOSS["name"], LOSS["metric"], TRIM, 5.0, 1e-12, ITERS, True, 0.0)
+    s = src.detach().clone().requires_grad_(True)
+    t = tgt.detach().clone().requires_grad_(True)
+    w = torch.ones((N, n), device=dev, requires_grad=True) if with_weight else None
+    T0 = torch.eye(4, device=dev).repeat(N, 1, 1)
+    outs = _functions.ICPFunction.apply(s, t, T0, w, p)
+    ctx = outs[1].grad_fn
+    source, target, w_init, saved_idx, saved_state = ctx.saved_tensors
+    g_T = torch.zeros((N, 4, 4), device=dev)
+    g_T[:, :3, :] = torch.arange(1, 13, dtype=torch.float32, device=dev).reshape(3, 4)
+    g_src, g_tgt, g_T0 = torch.empty_like(source), torch.empty_like(target), torch.empty((N, 4, 4), device=dev)
+    g_w = torch.empty((N, n), device=dev) if with_weight else None
+    st = _lib.stream_ptr(dev)
+
+    def launch(k):
+        _lib.check(lib.dicp_icp_backward_f32(_lib.ptr(source), _lib.ptr(target), _lib.ptr(w_init) if with_weight else None, N, n, m, 6,
+                                             ctypes.byref(p), k, _lib.ptr(saved_idx), _lib.ptr(saved_state), _lib.ptr(g_T), None,
+                                             _lib.ptr(g_src), _lib.ptr(g_tgt), _lib.ptr(g_w), _lib.ptr(g_T0), _lib.ptr(ctx.ws), ctx.ws.numel(), st), "bwd")
+
+    t10 = time_kernel(lambda: launch(ITERS), reps=5)
+    t5 = time_kernel(lambda: launch(ITERS // 2), reps=5)
+    sec = (t10 - t5) / (ITERS - ITERS // 2)
+    per = 124.0 if with_weight else 112.0
+    # SURVEY.md 8(d): read p 12 + row 24 + idx 4 (+ w_init 4), RMW grad_source 24 (+ grad_w 8), atomic RMW grad_target 48
+    nbytes = per * N * n
+    ach = nbytes / sec / 1e9
+    return {"kernel": "bwd_points_staged_kernel<pt2pl> + bwd_pair_kernel, one reverse iteration", "bound": "hbm", "achieved": ach,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "ms_per_launch": sec * 1e3,
+            "bytes_per_correspondence": per, "with_weight_gradient": with_weight, "units_per_launch": float(N) * n, "pairs": N,
+            "whole_backward_ms": t10 * 1e3, "peak_source": pk["source"]}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from dicp_b200.ICP import ICP          # `dICP.ICP.ICP` of the drop-in alias package is this class

@@ -11,12 +11,45 @@
 //                      += into grad_source and grad_w (private rows, plain RMW),
 //                      atomicAdd into grad_target[idx] (the scatter-add adjoint of the
 //                      gather, nn.py:37-38), CTA partial sums of sum(abar p^T), sum(ebar).
-// HBM-bound: 124 B per correspondence (pt2pl).
+// HBM-bound: 124 B per correspondence (pt2pl).  The point pass runs on the persistent tile schedule and the
+// TMA-fed staging ring of tile_stream.cuh (see gn_kernels.cu for the forward twin); its scatter goes to a
+// 16-byte aligned gradient table (8 floats per target row, 4 for point-to-point) with 128-bit vector reductions
+// (red.global.add.v4.f32: two per correspondence instead of three 64-bit ones on rows that straddle sectors), which
+// one pass folds into the caller's [N,m,S] gradient at the end of the reverse loop.
 #include "common.cuh"
+#include "tile_stream.cuh"
 
 namespace dicp {
 
 constexpr int BW_THREADS = 128;
+#ifndef BW_U
+#define BW_U 2
+#endif
+#ifndef BW_STAGES
+#define BW_STAGES 4
+#endif
+#ifndef BW_MINB
+#define BW_MINB 3
+#endif
+#ifndef BW_K
+#define BW_K 2            // 512-correspondence chunks: the read-modify-write of the gradient table wants tight locality (k = 8: 641 us, k = 2: 461 us at 1024 pairs)
+#endif
+#ifndef BW_GTAB
+#define BW_GTAB 1          // 1: scatter into the aligned gradient table (two red.v4.f32), 0: into the caller's rows (three red.v2.f32)
+#endif
+constexpr int BW_TILE = BW_THREADS * BW_U;
+constexpr int BW_STAGE_BYTES = BW_TILE * 36;      // idx 4 + p 12 + w0 4 + grad_source 12 + grad_w 4 per correspondence
+
+TilePlan bw_tile_plan(int N, int n) { return make_tile_plan(N, n, BW_TILE, BW_MINB, BW_K); }
+int bw_seed_blocks(int n) {                      // the seed pass: one partial row per CTA, up to 128 CTAs per pair
+  int nb = (n + 1023) / 1024;
+  return nb < 1 ? 1 : (nb > 128 ? 128 : nb);
+}
+int bw_rows_per_pair(int N, int n) {             // rows of the [N, rows, BW_NRED] partial-sum table
+  const int a = bw_tile_plan(N, n).rows, b = bw_seed_blocks(n);
+  return a > b ? a : b;
+}
+size_t bw_gtab_bytes(int N, int m, int elem_size) { return elem_size == 4 ? (size_t)N * m * 32 : 0; }
 
 template <typename T, int NV>
 __device__ __forceinline__ void bw_block_reduce_store(const T* vals, double* out, double* smem) {
@@ -75,32 +108,40 @@ bwd_seed_kernel(const T* __restrict__ source, const T* __restrict__ grad_pc, con
 // mode 0: first step (k = K-1): carry = grad_T + partial sums, then update-step adjoint
 // mode 1: later steps:          carry += partial sums,          then update-step adjoint
 // mode 2: after k = 0:          carry += partial sums, write grad_T_init
+// One warp per pair: lanes 0..11 each own one component of the carry (Cbar 9, rbar 3) and add up the partial rows
+// (coalesced 96-byte row reads, fixed order), lane 0 then runs the serial 3x3 / 6x6 algebra in double.
 template <typename T>
-__global__ void bwd_pair_kernel(const double* __restrict__ partials, int nblk, const double* __restrict__ rec_k, int dim, int mode,
-                                const T* __restrict__ grad_T, double* __restrict__ bw_state, T* __restrict__ grad_T_init, int N) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+bwd_pair_kernel(const double* __restrict__ partials, int nblk, int row_stride, const double* __restrict__ rec_k, int dim, int mode,
+                const T* __restrict__ grad_T, double* __restrict__ bw_state, T* __restrict__ grad_T_init, int N) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= N) return;
   double* bw = bw_state + (size_t)b * BW_STRIDE;
-  double carry[12];
-  if (mode == 0) {
-    for (int rr = 0; rr < 3; ++rr) {
-      for (int c = 0; c < 3; ++c) carry[rr * 3 + c] = grad_T != nullptr ? (double)grad_T[(size_t)b * 16 + rr * 4 + c] : 0.0;
-      carry[9 + rr] = grad_T != nullptr ? (double)grad_T[(size_t)b * 16 + rr * 4 + 3] : 0.0;
+  double mine = 0.0;
+  if (lane < 12) {
+    if (mode == 0) {
+      const int rr = lane < 9 ? lane / 3 : lane - 9, c = lane < 9 ? lane % 3 : 3;
+      mine = grad_T != nullptr ? (double)grad_T[(size_t)b * 16 + rr * 4 + c] : 0.0;
+    } else {
+      mine = bw[lane];
     }
-  } else {
-    for (int i = 0; i < 12; ++i) carry[i] = bw[i];
+    const double* rows_b = partials + (size_t)b * row_stride * BW_NRED + lane;
+    for (int j = 0; j < nblk; ++j) mine += rows_b[(size_t)j * BW_NRED];
   }
-  for (int j = 0; j < nblk; ++j)
-    for (int i = 0; i < 12; ++i) carry[i] += partials[((size_t)b * nblk + j) * BW_NRED + i];
   if (mode == 2) {
-    T* g = grad_T_init + (size_t)b * 16;
-    for (int rr = 0; rr < 3; ++rr) {
-      for (int c = 0; c < 3; ++c) g[rr * 4 + c] = (T)carry[rr * 3 + c];
-      g[rr * 4 + 3] = (T)carry[9 + rr];
+    if (lane < 12) {
+      const int rr = lane < 9 ? lane / 3 : lane - 9, c = lane < 9 ? lane % 3 : 3;
+      grad_T_init[(size_t)b * 16 + rr * 4 + c] = (T)mine;
+    } else if (lane < 16) {
+      grad_T_init[(size_t)b * 16 + 12 + (lane - 12)] = T(0);
     }
-    g[12] = g[13] = g[14] = g[15] = T(0);
     return;
   }
+  double carry[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) carry[i] = __shfl_sync(0xffffffffu, mine, i);
+  if (lane != 0) return;
   const double* rec = rec_k + (size_t)b * ST_STRIDE;
   double lam[6] = {0, 0, 0, 0, 0, 0};
   const double active = rec[ST_ACTIVE];
@@ -112,82 +153,333 @@ __global__ void bwd_pair_kernel(const double* __restrict__ partials, int nblk, c
   bw[BW_ACTIVE] = active;
 }
 
-template <typename T, bool PT2PL, bool FASTW>
-__global__ void __launch_bounds__(BW_THREADS)
-bwd_points_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
-                  const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
-                  int n, int m, int S, WeightParams P, T* __restrict__ grad_source, T* __restrict__ grad_target,
-                  T* __restrict__ grad_w, double* __restrict__ partials) {
-  __shared__ double red_smem[(BW_THREADS / 32) * BW_NRED];
-  const int b = blockIdx.y;
-  const double* rec = rec_k + (size_t)b * ST_STRIDE;
-  const double* bw = bw_state + (size_t)b * BW_STRIDE;
-  T acc[BW_NRED];
+// per-segment hand-over of the 12 partial sums (sum abar p^T, sum ebar), same row numbering as the forward
+template <typename T>
+__device__ __forceinline__ void bw_flush_segment(const TilePlan& plan, int nrows, int b, long long seg_tile, long long last_tile,
+                                                 const T* acc, double* __restrict__ partials, double* red_smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int row = tp_segment_row(plan, b, seg_tile);
+  double* rows_b = partials + (size_t)b * nrows * BW_NRED;
+  T v[32];
 #pragma unroll
-  for (int i = 0; i < BW_NRED; ++i) acc[i] = T(0);
-  if (bw[BW_ACTIVE] != 0.0) {
-    T C[9], r[3], lam[6], del[6];
+  for (int i = 0; i < BW_NRED; ++i) v[i] = acc[i];
+  warp_multi_reduce<T, BW_NRED>(v);
+  red_smem[warp * 32 + lane] = (double)v[0];
+  __syncthreads();
+  if (threadIdx.x < BW_NRED) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += red_smem[w * 32 + threadIdx.x];
+    rows_b[(size_t)row * BW_NRED + threadIdx.x] = s;
+  }
+  if (last_tile == (long long)b * plan.tpp + plan.tpp - 1) {
+    for (int i = (row + 1) * BW_NRED + threadIdx.x; i < nrows * BW_NRED; i += blockDim.x) rows_b[i] = 0.0;
+  }
+  __syncthreads();
+}
+
+// what the point pass needs to know about a pair in iteration k
+template <typename T>
+struct BwPairCtx {
+  T C[9], r[3], lam[6], del[6];
+  bool active;
+  int b;
+  long long seg_tile;
+};
+
+// scatter-add of one correspondence's target gradient into the aligned table (fp32 fast path)
+template <bool PT2PL>
+__device__ __forceinline__ void scatter_gtab(float* __restrict__ gtab, size_t row, const float* ebar, const float* nbar) {
+  if (PT2PL) {
+    float4* g = reinterpret_cast<float4*>(gtab) + row * 2;
+    atomicAdd(g, make_float4(-ebar[0], -ebar[1], -ebar[2], nbar[0]));
+    atomicAdd(g + 1, make_float4(nbar[1], nbar[2], 0.0f, 0.0f));
+  } else {
+    atomicAdd(reinterpret_cast<float4*>(gtab) + row, make_float4(-ebar[0], -ebar[1], -ebar[2], 0.0f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 fast path (n % 4 == 0, 16-byte aligned streams, gather table `rows` and gradient table `gtab` present).
+// Ring stage = { idx | p | w0 | grad_source | grad_w } slices of the tile; see gn_accum_staged_kernel for the
+// full / empty barrier protocol, the rotating feeder and the state prefetch.
+// ---------------------------------------------------------------------------------------------------------
+template <bool PT2PL, bool FASTW>
+__global__ void __launch_bounds__(BW_THREADS, BW_MINB)
+bwd_points_staged_kernel(const float* __restrict__ source, const void* __restrict__ rows, const float* __restrict__ w_init,
+                         const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
+                         int n, int m, WeightParams P, float* __restrict__ grad_source, float* __restrict__ gtab,
+                         float* __restrict__ grad_w, double* __restrict__ partials, int nrows, TilePlan plan, int gS) {
+  constexpr int U = BW_U, TILE = BW_TILE, STAGES = BW_STAGES, WARPS = BW_THREADS / 32;
+  static_assert(STAGES >= 3, "a stage is refilled one step after its release");
+  extern __shared__ __align__(128) unsigned char bw_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto st_idx = [&](int s) { return reinterpret_cast<int32_t*>(bw_smem + (size_t)s * BW_STAGE_BYTES); };
+  auto st_p = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 4); };
+  auto st_w = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 16); };
+  auto st_gs = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 20); };
+  auto st_gw = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 32); };
+  double* red_smem = reinterpret_cast<double*>(bw_smem + (size_t)STAGES * BW_STAGE_BYTES);
+  double* slot = red_smem + WARPS * 32 + warp * 32;            // this warp's copy of the next segment's pair record
+  uint64_t* full = reinterpret_cast<uint64_t*>(red_smem + WARPS * 32 + WARPS * 32);
+  uint64_t* empty = full + STAGES;
+  TileWalk walk;
+  walk.init(plan, blockIdx.x);
+  const int ntiles = walk.ntiles;
+  if (ntiles == 0) return;
+  if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) C[i] = (T)rec[ST_C + i];
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  typedef TileCursor Cursor;
+  auto tile_count = [&](const Cursor& c) { return min(TILE, n - c.j * TILE); };
+  auto issue = [&](const Cursor& c) {
+    const int s = c.L % STAGES;
+    const uint32_t cnt = (uint32_t)tile_count(c);
+    const size_t o = (size_t)c.b * n + c.j * TILE;
+    mbar_expect_tx(&full[s], cnt * (28u + (w_init != nullptr ? 4u : 0u) + (grad_w != nullptr ? 4u : 0u)));
+    bulk_g2s(st_idx(s), idx + o, cnt * 4u, &full[s]);
+    bulk_g2s(st_p(s), source + o * 3, cnt * 12u, &full[s]);
+    bulk_g2s(st_gs(s), grad_source + o * 3, cnt * 12u, &full[s]);
+    if (w_init != nullptr) bulk_g2s(st_w(s), w_init + o, cnt * 4u, &full[s]);
+    if (grad_w != nullptr) bulk_g2s(st_gw(s), grad_w + o, cnt * 4u, &full[s]);
+  };
+  // (C 9, r 3) of the iteration and (lambda 6, delta 6, active) of the reverse step into the warp's slot
+  auto prefetch_state = [&](int b) {
+    const double* rec = rec_k + (size_t)b * ST_STRIDE;
+    const double* bw = bw_state + (size_t)b * BW_STRIDE;
+    if (lane < 12) cp_async8(slot + lane, rec + (lane < 9 ? ST_C + lane : ST_R + lane - 9));
+    else if (lane < 24) cp_async8(slot + lane, bw + BW_LAM + (lane - 12));       // BW_LAM .. BW_DEL + 5 are contiguous
+    else if (lane == 24) cp_async8(slot + 24, bw + BW_ACTIVE);
+  };
+  static_assert(BW_DEL == BW_LAM + 6, "lambda and delta are fetched as one run");
+
+  struct Gathered { float q[U][3], nr[U][3]; int jj[U]; };
+  auto gather = [&](const Cursor& c, Gathered& g) {
+    const int s = c.L % STAGES;
+    const int cnt = tile_count(c);
+    mbar_wait(&full[s], (uint32_t)((c.L / STAGES) & 1));
+    const size_t row_b = (size_t)c.b * m;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) r[i] = (T)rec[ST_R + i];
+    for (int u = 0; u < U; ++u) {
+      const int j = tid * U + u < cnt ? st_idx(s)[tid * U + u] : 0;
+      g.jj[u] = j;
+      load_packed_row<float, PT2PL>(rows, row_b + j, g.q[u], g.nr[u]);
+    }
+  };
+
+  float acc[BW_NRED];
+  BwPairCtx<float> ctx;
+  ctx.b = -1;
+  ctx.active = false;
+  long long last_tile = 0;
+  auto enter = [&](const Cursor& c) {
+    if (c.L > 0) bw_flush_segment<float>(plan, nrows, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
+    cp_async_wait_all();
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { lam[i] = (T)bw[BW_LAM + i]; del[i] = (T)bw[BW_DEL + i]; }
-    const T* src_b = source + (size_t)b * n * 3;
-    const T* tgt_b = target + (size_t)b * m * S;
-    T* gt_b = grad_target + (size_t)b * m * S;
-    T* gs_b = grad_source + (size_t)b * n * 3;
-    const int32_t* idx_b = idx + (size_t)b * n;
-    // U correspondences per thread and pass, loads hoisted ahead of the arithmetic (see gn_accum_kernel)
-    constexpr int U = sizeof(T) == 4 ? 4 : 2;
-    for (int base = blockIdx.x * (BW_THREADS * U); base < n; base += gridDim.x * (BW_THREADS * U)) {
-      int ii[U], jj[U];
-      T p[U][3], q[U][3], nr[U][3], w0[U], gs[U][3], gw[U];
+    for (int i = 0; i < 9; ++i) ctx.C[i] = (float)slot[i];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = base + u * BW_THREADS + threadIdx.x;
-        ii[u] = i < n ? i : -1;
-        const int ic = i < n ? i : n - 1;
-        jj[u] = idx_b[ic];
-        p[u][0] = src_b[3 * ic]; p[u][1] = src_b[3 * ic + 1]; p[u][2] = src_b[3 * ic + 2];
-        w0[u] = w_init != nullptr ? w_init[(size_t)b * n + ic] : T(1);
-        // the running gradients this pass adds to: read with the other loads, not after the arithmetic
-        gs[u][0] = gs_b[3 * ic]; gs[u][1] = gs_b[3 * ic + 1]; gs[u][2] = gs_b[3 * ic + 2];
-        gw[u] = grad_w != nullptr ? grad_w[(size_t)b * n + ic] : T(0);
+    for (int i = 0; i < 3; ++i) ctx.r[i] = (float)slot[9 + i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { ctx.lam[i] = (float)slot[12 + i]; ctx.del[i] = (float)slot[18 + i]; }
+    ctx.active = slot[24] != 0.0;
+    ctx.b = c.b;
+    ctx.seg_tile = c.tile(plan);
+#pragma unroll
+    for (int i = 0; i < BW_NRED; ++i) acc[i] = 0.0f;
+    __syncwarp();
+  };
+
+  Cursor ci, cg;
+  ci.init(plan, walk);
+  cg.init(plan, walk);
+  auto step = [&](const Gathered& gc, Gathered& gn) {
+    const Cursor cc = cg;
+    if (cc.seg_first) enter(cc);
+    last_tile = cc.tile(plan);
+    const int s = cc.L % STAGES;
+    const int cnt = tile_count(cc);
+    // this lane's staged inputs
+    float p[U][3], gs[U][3], w0[U], gw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { p[u][c] = st_p(s)[(tid * U + u) * 3 + c]; gs[u][c] = st_gs(s)[(tid * U + u) * 3 + c]; }
+      w0[u] = w_init != nullptr ? st_w(s)[tid * U + u] : 1.0f;
+      gw[u] = grad_w != nullptr ? st_gw(s)[tid * U + u] : 0.0f;
+    }
+    cg.next(plan, walk);
+    if (cg.L < ntiles) {
+      if (cg.seg_first) prefetch_state(cg.b);
+      gather(cg, gn);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (ci.L < ntiles) {
+      if (warp == (ci.L % WARPS) && lane == 0) {
+        if (ci.L >= STAGES) mbar_wait(&empty[ci.L % STAGES], (uint32_t)((ci.L / STAGES - 1) & 1));
+        issue(ci);
       }
+      ci.next(plan, walk);
+    }
+    if (!ctx.active) return;                  // frozen pair: nothing flows into its points (ICP.py:256-257)
+    const size_t o = (size_t)cc.b * n + cc.j * TILE + tid * U;
+    const size_t row_b = (size_t)cc.b * m;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        load_target_row<T, PT2PL>(tgt_b + (size_t)jj[u] * S, S, q[u], nr[u]);
-      }
+    for (int u = 0; u < U; ++u) {
+      if (tid * U + u >= cnt) continue;
+      PointEval<float> ev;
+      eval_point<float, PT2PL, FASTW>(ctx.C, ctx.r, p[u], gc.q[u], gc.nr[u], w0[u], P, ev);
+      float abar[3], ebar[3], nbar[3], w0bar;
+      point_backward<float, PT2PL>(ev, w0[u], ctx.lam, ctx.del, abar, ebar, nbar, w0bar);
+      if (grad_w != nullptr) grad_w[o + u] = gw[u] + w0bar;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (ii[u] < 0) continue;
-        const int i = ii[u];
-        PointEval<T> s;
-        eval_point<T, PT2PL, FASTW>(C, r, p[u], q[u], nr[u], w0[u], P, s);
-        T abar[3], ebar[3], nbar[3], w0bar;
-        point_backward<T, PT2PL>(s, w0[u], lam, del, abar, ebar, nbar, w0bar);
-        if (grad_w != nullptr) grad_w[(size_t)b * n + i] = gw[u] + w0bar;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) gs_b[3 * i + c] = gs[u][c] + (C[c] * abar[0] + C[3 + c] * abar[1] + C[6 + c] * abar[2]);   // C^T abar
-        T* grow = gt_b + (size_t)jj[u] * S;
+      for (int c = 0; c < 3; ++c)
+        grad_source[(o + u) * 3 + c] = gs[u][c] + (ctx.C[c] * abar[0] + ctx.C[3 + c] * abar[1] + ctx.C[6 + c] * abar[2]);   // C^T abar
+      if (BW_GTAB) {
+        scatter_gtab<PT2PL>(gtab, row_b + gc.jj[u], ebar, nbar);
+      } else {                                 // gtab is the caller's [N,m,S] gradient here, S = 6 | 3
+        float* grow = gtab + (row_b + gc.jj[u]) * (PT2PL ? 6 : gS);
         if (PT2PL) {
-          const T g6[6] = {-ebar[0], -ebar[1], -ebar[2], nbar[0], nbar[1], nbar[2]};
+          const float g6[6] = {-ebar[0], -ebar[1], -ebar[2], nbar[0], nbar[1], nbar[2]};
           atomic_add_row6(grow, g6);
         } else {
 #pragma unroll
           for (int c = 0; c < 3; ++c) atomicAdd(grow + c, -ebar[c]);
         }
+      }
 #pragma unroll
-        for (int rr = 0; rr < 3; ++rr) {
+      for (int rr = 0; rr < 3; ++rr) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) acc[rr * 3 + c] += abar[rr] * p[u][c];
-          acc[9 + rr] += ebar[rr];
-        }
+        for (int c = 0; c < 3; ++c) acc[rr * 3 + c] += abar[rr] * p[u][c];
+        acc[9 + rr] += ebar[rr];
+      }
+    }
+  };
+
+  if (tid == 0) issue(ci);
+  ci.next(plan, walk);
+  prefetch_state(cg.b);
+  Gathered ga, gb;
+  gather(cg, ga);
+  if (tid == 0) {
+    for (int s = 1; s < STAGES - 1 && ci.L < ntiles; ++s) { issue(ci); ci.next(plan, walk); }
+  }
+  {
+    const int target_L = min(STAGES - 1, ntiles);
+    Cursor t;
+    t.init(plan, walk);
+    while (t.L < target_L) t.next(plan, walk);
+    ci = t;
+  }
+#pragma unroll 1
+  for (;;) {
+    step(ga, gb);
+    if (cg.L >= ntiles) break;
+    step(gb, ga);
+    if (cg.L >= ntiles) break;
+  }
+  bw_flush_segment<float>(plan, nrows, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic path (fp64, or fp32 inputs that do not meet the alignment rules): same schedule and partial rows,
+// plain loads, scatter straight into the caller's gradient rows.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool PT2PL, bool FASTW>
+__global__ void __launch_bounds__(BW_THREADS)
+bwd_points_generic_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
+                          const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
+                          int n, int m, int S, WeightParams P, T* __restrict__ grad_source, T* __restrict__ grad_target,
+                          T* __restrict__ grad_w, double* __restrict__ partials, int nrows, TilePlan plan) {
+  __shared__ double red_smem[(BW_THREADS / 32) * 32];
+  TileWalk walk;
+  walk.init(plan, blockIdx.x);
+  const int ntiles = walk.ntiles;
+  if (ntiles == 0) return;
+  T acc[BW_NRED];
+  BwPairCtx<T> ctx;
+  ctx.b = -1;
+  ctx.active = false;
+  long long last_tile = 0;
+  TileCursor c;
+  for (c.init(plan, walk); c.L < ntiles; c.next(plan, walk)) {
+    const int b = c.b;
+    if (c.seg_first) {
+      if (c.L > 0) bw_flush_segment<T>(plan, nrows, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
+      const double* rec = rec_k + (size_t)b * ST_STRIDE;
+      const double* bw = bw_state + (size_t)b * BW_STRIDE;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) ctx.C[i] = (T)rec[ST_C + i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ctx.r[i] = (T)rec[ST_R + i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { ctx.lam[i] = (T)bw[BW_LAM + i]; ctx.del[i] = (T)bw[BW_DEL + i]; }
+      ctx.active = bw[BW_ACTIVE] != 0.0;
+      ctx.b = b;
+      ctx.seg_tile = c.tile(plan);
+#pragma unroll
+      for (int i = 0; i < BW_NRED; ++i) acc[i] = T(0);
+    }
+    last_tile = c.tile(plan);
+    if (!ctx.active) continue;
+    const T* src_b = source + (size_t)b * n * 3;
+    const T* tgt_b = target + (size_t)b * m * S;
+    T* gt_b = grad_target + (size_t)b * m * S;
+    T* gs_b = grad_source + (size_t)b * n * 3;
+    const int i0 = c.j * plan.tile, i_end = min(i0 + plan.tile, n);
+    for (int i = i0 + threadIdx.x; i < i_end; i += BW_THREADS) {
+      const int j = idx[(size_t)b * n + i];
+      const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
+      const T w0 = w_init != nullptr ? w_init[(size_t)b * n + i] : T(1);
+      T q[3], nr[3];
+      load_target_row<T, PT2PL>(tgt_b + (size_t)j * S, S, q, nr);
+      PointEval<T> ev;
+      eval_point<T, PT2PL, FASTW>(ctx.C, ctx.r, p, q, nr, w0, P, ev);
+      T abar[3], ebar[3], nbar[3], w0bar;
+      point_backward<T, PT2PL>(ev, w0, ctx.lam, ctx.del, abar, ebar, nbar, w0bar);
+      if (grad_w != nullptr) grad_w[(size_t)b * n + i] += w0bar;
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) gs_b[3 * i + cc] += ctx.C[cc] * abar[0] + ctx.C[3 + cc] * abar[1] + ctx.C[6 + cc] * abar[2];   // C^T abar
+      T* grow = gt_b + (size_t)j * S;
+      if (PT2PL) {
+        const T g6[6] = {-ebar[0], -ebar[1], -ebar[2], nbar[0], nbar[1], nbar[2]};
+        atomic_add_row6(grow, g6);
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) atomicAdd(grow + cc, -ebar[cc]);
+      }
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) acc[rr * 3 + cc] += abar[rr] * p[cc];
+        acc[9 + rr] += ebar[rr];
       }
     }
   }
-  bw_block_reduce_store<T, BW_NRED>(acc, partials + ((size_t)b * gridDim.x + blockIdx.x) * BW_NRED, red_smem);
+  bw_flush_segment<T>(plan, nrows, ctx.b, ctx.seg_tile, last_tile, acc, partials, red_smem);
+}
+
+// folds the aligned gradient table into the caller's [N,m,S] rows (every entry is written)
+template <bool PT2PL>
+__global__ void __launch_bounds__(256)
+bwd_unpack_gtab_kernel(const float* __restrict__ gtab, size_t total, int S, float* __restrict__ grad_target) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float* g = grad_target + i * S;
+    if (PT2PL) {
+      const float4 a = reinterpret_cast<const float4*>(gtab)[2 * i], b = reinterpret_cast<const float4*>(gtab)[2 * i + 1];
+      *reinterpret_cast<float2*>(g) = make_float2(a.x, a.y);
+      *reinterpret_cast<float2*>(g + 2) = make_float2(a.z, a.w);
+      *reinterpret_cast<float2*>(g + 4) = make_float2(b.x, b.y);
+    } else {
+      const float4 a = reinterpret_cast<const float4*>(gtab)[i];
+      g[0] = a.x; g[1] = a.y; g[2] = a.z;
+      for (int c = 3; c < S; ++c) g[c] = 0.0f;
+    }
+  }
 }
 
 template <typename T>
@@ -206,32 +498,78 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
   IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T));
   const WeightParams P = make_weight_params(p);
   const bool fast = weight_params_fast(P);
-  const int nblk = bw_blocks_per_pair(n);
+  const TilePlan plan = bw_tile_plan(N, n);
+  const int nseed = bw_seed_blocks(n), nrows = bw_rows_per_pair(N, n);
   const size_t rec_stride = (size_t)N * ST_STRIDE;
   const bool pl = p->icp_type == DICP_PT2PL;
-  dim3 pgrid(nblk, N);
-  const int pair_blocks = (N + 127) / 128;
+  const int pair_blocks = (N + 3) / 4;         // one warp per pair
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  // fast path: the streams move as 16-byte aligned slices; the gather table is rebuilt here (the workspace of the
+  // forward call may have been reused in between), the gradient table lives in the workspace
+  const bool staged = sizeof(T) == 4 && (n % 4) == 0 && aligned16(source) && aligned16(saved_idx) && aligned16(w_init) &&
+                      aligned16(grad_source) && aligned16(grad_w) && (((size_t)N * n) % 4) == 0;
 
-  DICP_CUDA(cudaMemsetAsync(grad_target, 0, (size_t)N * m * S * sizeof(T), st));
+  if (staged) {
+    int rc = gn_pack_rows<T>(target, N, m, S, pl, w.rows, st);
+    if (rc) return rc;
+    if (BW_GTAB) DICP_CUDA(cudaMemsetAsync(w.gtab, 0, (size_t)N * m * (pl ? 32 : 16), st));
+    else DICP_CUDA(cudaMemsetAsync(grad_target, 0, (size_t)N * m * S * sizeof(T), st));
+  } else {
+    DICP_CUDA(cudaMemsetAsync(grad_target, 0, (size_t)N * m * S * sizeof(T), st));
+  }
   if (grad_w != nullptr) DICP_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)N * n * sizeof(T), st));
-  bwd_seed_kernel<T><<<pgrid, BW_THREADS, 0, st>>>(source, grad_pc, saved_state + (size_t)iters_run * rec_stride, n, grad_source, w.bw_partials);
+  bwd_seed_kernel<T><<<dim3(nseed, N), BW_THREADS, 0, st>>>(source, grad_pc, saved_state + (size_t)iters_run * rec_stride, n, grad_source, w.bw_partials);
   DICP_LAUNCH_CHECK();
+  constexpr size_t smem = (size_t)BW_STAGES * BW_STAGE_BYTES + (BW_THREADS / 32) * 64 * sizeof(double) + 2 * BW_STAGES * sizeof(uint64_t);
   for (int k = iters_run - 1; k >= 0; --k) {
     const double* rec_k = saved_state + (size_t)k * rec_stride;
-    bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, nblk, rec_k, p->dim, k == iters_run - 1 ? 0 : 1, grad_T, w.bw_state, grad_T_init, N);
+    const bool first = k == iters_run - 1;
+    // the first reverse step folds the seed pass's rows (one per seed CTA, contiguous), later ones the point pass's
+    bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, first ? nseed : nrows, first ? nseed : nrows, rec_k, p->dim, first ? 0 : 1,
+                                                    grad_T, w.bw_state, grad_T_init, N);
     DICP_LAUNCH_CHECK();
     const int32_t* idx_k = saved_idx + (size_t)k * N * n;
-#define DICP_BW_LAUNCH(PL, FW) \
-  bwd_points_kernel<T, PL, FW><<<pgrid, BW_THREADS, 0, st>>>(source, target, w_init, idx_k, rec_k, w.bw_state, n, m, S, P, grad_source, grad_target, grad_w, w.bw_partials)
-    if (pl && fast) DICP_BW_LAUNCH(true, true);
-    else if (pl) DICP_BW_LAUNCH(true, false);
-    else if (fast) DICP_BW_LAUNCH(false, true);
-    else DICP_BW_LAUNCH(false, false);
+    if (staged) {
+      if constexpr (sizeof(T) == 4) {
+#define DICP_BW_LAUNCH(PL, FW)                                                                                                     \
+  do {                                                                                                                             \
+    static bool attr_set = false;                                                                                                  \
+    if (!attr_set) {                                                                                                               \
+      DICP_CUDA(cudaFuncSetAttribute(bwd_points_staged_kernel<PL, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+      attr_set = true;                                                                                                             \
+    }                                                                                                                              \
+    bwd_points_staged_kernel<PL, FW><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
+                                                                         grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w, w.bw_partials, nrows, plan, S); \
+  } while (0)
+        if (pl && fast) DICP_BW_LAUNCH(true, true);
+        else if (pl) DICP_BW_LAUNCH(true, false);
+        else if (fast) DICP_BW_LAUNCH(false, true);
+        else DICP_BW_LAUNCH(false, false);
 #undef DICP_BW_LAUNCH
+      }
+    } else {
+#define DICP_BW_LAUNCH(PL, FW)                                                                                                     \
+  bwd_points_generic_kernel<T, PL, FW><<<plan.ctas, BW_THREADS, 0, st>>>(source, target, w_init, idx_k, rec_k, w.bw_state, n, m, S, P, \
+                                                                        grad_source, grad_target, grad_w, w.bw_partials, nrows, plan)
+      if (pl && fast) DICP_BW_LAUNCH(true, true);
+      else if (pl) DICP_BW_LAUNCH(true, false);
+      else if (fast) DICP_BW_LAUNCH(false, true);
+      else DICP_BW_LAUNCH(false, false);
+#undef DICP_BW_LAUNCH
+    }
     DICP_LAUNCH_CHECK();
   }
-  bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, nblk, saved_state, p->dim, 2, grad_T, w.bw_state, grad_T_init, N);
+  bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, nrows, nrows, saved_state, p->dim, 2, grad_T, w.bw_state, grad_T_init, N);
   DICP_LAUNCH_CHECK();
+  if (staged && BW_GTAB) {
+    if constexpr (sizeof(T) == 4) {
+      const size_t total = (size_t)N * m;
+      const int grid = (int)((total + 255) / 256 < (size_t)device_sm_count() * 16 ? (total + 255) / 256 : (size_t)device_sm_count() * 16);
+      if (pl) bwd_unpack_gtab_kernel<true><<<grid, 256, 0, st>>>((const float*)w.gtab, total, S, grad_target);
+      else bwd_unpack_gtab_kernel<false><<<grid, 256, 0, st>>>((const float*)w.gtab, total, S, grad_target);
+      DICP_LAUNCH_CHECK();
+    }
+  }
   return 0;
 }
 

@@ -191,7 +191,8 @@ int grid_search(const T* q, const double* state, int N, int n, int m, const Grid
 
 // ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------
 int gn_blocks_per_pair(int N, int n);   // partial-sum rows per pair of the accumulate kernel's tile plan (tile_stream.cuh)
-int bw_blocks_per_pair(int n);
+int bw_rows_per_pair(int N, int n);      // rows per pair of the backward's [N, rows, BW_NRED] partial-sum table
+size_t bw_gtab_bytes(int N, int m, int elem_size);   // fp32: aligned gradient table of the targets (8 floats per row)
 // where the accumulate kernel finds (C, r, active) of pair b: state + b * stride + {c, r, active}
 // (active < 0: every pair is active).  The loop passes its saved-state records, the stage API a bare [N,12].
 struct StateView { const double* base; int stride, c, r, active; };
@@ -220,6 +221,7 @@ struct IcpWorkspace {
   void* grid_ws;       // uniform-grid index of the targets (nn_mode == DICP_NN_GRID)
   size_t grid_ws_bytes;
   void* rows;          // fp32: [N, m] aligned gather records of the targets (gn_pack_rows); unused for fp64
+  void* gtab;          // fp32: [N, m] aligned gradient records of the targets (backward scatter); unused for fp64
   size_t total;
 };
 IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size);

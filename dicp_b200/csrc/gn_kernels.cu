@@ -67,12 +67,6 @@ int device_sm_count() {
 TilePlan gn_tile_plan(int N, int n) { return make_tile_plan(N, n, GN_TILE, GN_CTAS_PER_SM, GN_K); }
 int gn_blocks_per_pair(int N, int n) { return gn_tile_plan(N, n).rows; }
 
-int bw_blocks_per_pair(int n) {          // backward point pass: 8 correspondences per thread (2 passes of 4)
-  int nb = (n + 1023) / 1024;
-  if (nb < 1) nb = 1;
-  if (nb > 128) nb = 128;
-  return nb;
-}
 
 // block-wide sum of NV (<= 32) per-thread values: per warp a 31-shuffle multi-value reduction in the compute type
 // (tile_stream.cuh), then double across warps; result lands in out[0..NV) of the segment's partial row.
@@ -641,10 +635,11 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
   w.partials = ar.take<double>((size_t)N * gn_blocks_per_pair(N, n) * RED_N);
   w.ctrl = ar.take<Ctrl>(1);
   w.bw_state = ar.take<double>((size_t)N * BW_STRIDE);
-  w.bw_partials = ar.take<double>((size_t)N * bw_blocks_per_pair(n) * BW_NRED);
+  w.bw_partials = ar.take<double>((size_t)N * bw_rows_per_pair(N, n) * BW_NRED);
   w.grid_ws_bytes = grid_ws_layout(nullptr, 0, N, n, m, elem_size).total;
   w.grid_ws = ar.take<char>(w.grid_ws_bytes);
   w.rows = ar.take<char>(gn_rows_bytes(N, m, elem_size) > 0 ? gn_rows_bytes(N, m, elem_size) : 1);
+  w.gtab = ar.take<char>(bw_gtab_bytes(N, m, elem_size) > 0 ? bw_gtab_bytes(N, m, elem_size) : 1);
   w.total = ar.off;
   return w;
 }

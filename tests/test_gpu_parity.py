@@ -416,7 +416,8 @@ def test_config2_pt2pt_64x4096_forward():
     # batch == per-chunk loop (tests/test_ICP_inputs.py:106-107 at scale)
     with torch.no_grad():
         sub = icp.icp(src[5:9].cuda(), tgt[5:9].cuda(), torch.eye(4, device="cuda").repeat(4, 1, 1), dim=3)
-    assert torch.equal(sub["T"], res["T"][5:9])
+    # (not bit-identical: the persistent tile schedule sums a pair's partial rows in an order that depends on the batch size)
+    assert rel_err(sub["T"].cpu(), res["T"][5:9].cpu()) < 2e-6
     # the generator moved the source by Rz(0.02), t=(0.3,-0.2,0.05): ICP must undo it
     c, s = np.cos(0.02), np.sin(0.02)
     Rz = torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
