@@ -89,9 +89,22 @@ class ICP:
         # Parity tests replay them through the fp64 oracle (gradients are only comparable on equal correspondences)
         self.keep_correspondences = False
         self.last_correspondences = None
+        # optional YAML key dICP.functionality.svd (commented out upstream, config/dICP_config.yaml:15-16): point-to-point
+        # problems are solved by the Kabsch / SVD loop `pt2pt_dICP_SVD` instead of Gauss-Newton
+        self.use_svd = bool(func.get('svd', False))
+        self.svd_literal = False
 
     def icp(self, source, target, T_init, weight=None, trim_dist=None, loss_fn=None, dim=3):
+        if self.use_svd and self.icp_type == 'pt2pt':
+            return self._icp_svd(source, target, T_init)
         return self.dICP(source, target, T_init, weight, trim_dist, loss_fn, dim)
+
+    def _icp_svd(self, source, target, T_init):
+        """`functionality.svd`: the Kabsch / SVD solver behind the result dictionary of `icp()` (weights, trimming and
+        robust losses do not exist on this path upstream either, ICP.py:533-591)."""
+        source, target, T_init, _ = self.batch_size_handling(source, target, T_init, None)
+        pc, T = self.pt2pt_dICP_SVD(source, target[:, :, :3], T_init)
+        return {"pc": pc, "T": T}
 
     # ---------------------------------------------------------------------------------
     def dICP(self, source, target, T_init, weight=None, trim_dist=None, loss_fn=None, dim=3):
@@ -299,47 +312,35 @@ class ICP:
 
     # ---------------------------------------------------------------------------------
     def pt2pt_dICP_SVD(self, source, target, T_init, trim_dist=None, huber_delta=None, dim=3):
-        """Kabsch / SVD point-to-point ICP (ICP.py:533-591; "not yet integrated" upstream, so there is
-        no config key and `trim_dist`, `huber_delta`, `dim` are accepted and ignored as they are there).
+        """Kabsch / SVD point-to-point ICP (ICP.py:533-591; "not yet integrated" upstream, so `trim_dist`,
+        `huber_delta`, `dim` are accepted and ignored as they are there).  Optional YAML key
+        `dICP.functionality.svd: True` makes `icp()` of a 'pt2pt' object take this path.
 
         source (n,>=3) / target (m,>=3) / T_init (4,4) as in the reference, or batched (N,n,.), (N,m,.),
-        (N,4,4).  Returns (moved source, T).  Per iteration the nearest-neighbour search and the fused
-        centroid + cross-covariance reduction run as CUDA kernels (`dicp_nn_argmin_*`,
-        `dicp_kabsch_sums_*`); the 3x3 SVD, determinant fix and composition are O(1) per pair and use
-        torch, which also provides their gradients.
+        (N,4,4).  Returns (moved source, T).  The whole loop runs on the device behind one autograd node
+        (`_functions.KabschICPFunction`): per iteration the nearest-neighbour search, the fused centroid +
+        cross-covariance reduction, one thread per pair for the 3x3 SVD (one-sided Jacobi in double),
+        determinant fix and composition, and the convergence test; the reverse pass is hand-written
+        (adjoint of the SVD step included).  A batch stops when every pair is below the tolerance.
 
         Reference quirks kept: `T_init` is only composed into the returned transform and is not applied
         to the source before the first search (ICP.py:545-547); convergence compares the moved points
-        with the neighbours found before the move (ICP.py:585).  One defect is not kept: ICP.py:566-570
-        multiplies by V where the Kabsch rotation needs V^T (torch.svd returns V), which is only right
-        when V is symmetric, as on the planar test fixture; here R = U diag(1,1,det(U)det(V)) V^T."""
+        with the neighbours found before the move (ICP.py:585).  One defect is not kept by default:
+        ICP.py:566-570 multiplies by V where the Kabsch rotation needs V^T (torch.svd returns V), which is
+        only right when V is symmetric, as on the planar test fixture; here R = U diag(1,1,det(U)det(V)) V^T.
+        `self.svd_literal = True` switches to the reference's literal product U D V; its value depends on the
+        sign convention of the SVD routine (LAPACK's is not specified), so parity with the reference is only
+        defined where V = V^T."""
         single = source.dim() == 2
         ps = (source.unsqueeze(0) if single else source)[:, :, 0:3]
         tgt = (target.unsqueeze(0) if target.dim() == 2 else target)[:, :, 0:3]
         T = T_init.unsqueeze(0) if T_init.dim() == 2 else T_init
         out_dev = ps.device
         dev = self._compute_device(out_dev)
-        ps, tgt, T = ps.to(dev), tgt.to(dev).contiguous(), T.to(dev)
-        N, n = ps.shape[0], ps.shape[1]
-        eye_row = torch.zeros((N, 1, 4), dtype=ps.dtype, device=dev)
-        eye_row[:, 0, 3] = 1.0
-        ii = 0
-        for ii in range(self.max_iterations):
-            idx = _functions.nn_argmin(ps.detach(), tgt.detach())                          # ICP.py:553-555
-            sums = _functions.KabschSums.apply(ps, tgt, idx)                                # ICP.py:558-563
-            p_mean, q_mean = sums[:, 0:3] / n, sums[:, 3:6] / n
-            W = sums[:, 6:15].reshape(N, 3, 3) / n - q_mean.unsqueeze(2) * p_mean.unsqueeze(1)
-            U, _, Vh = torch.linalg.svd(W)                                                  # ICP.py:566
-            d = torch.det(U) * torch.det(Vh)
-            D = torch.diag_embed(torch.stack((torch.ones_like(d), torch.ones_like(d), d), dim=1))
-            C = U @ D @ Vh                                                                  # ICP.py:570 (with V^T)
-            r = q_mean.unsqueeze(2) - C @ p_mean.unsqueeze(2)                               # ICP.py:573
-            T = torch.cat((torch.cat((C, r), dim=2), eye_row), dim=1) @ T                   # ICP.py:577-578
-            ps = ps @ C.transpose(1, 2) + r.transpose(1, 2)                                 # ICP.py:581
-            nn_t = _functions.GatherRows.apply(tgt, idx)
-            if bool((((ps - nn_t) ** 2).sum(dim=(1, 2)) < self.tolerance).all()):           # ICP.py:585
-                break
+        ps, tgt, T = ps.to(dev).contiguous(), tgt.to(dev).contiguous(), T.to(dev).to(ps.dtype)
+        pc, T_out = _functions.KabschICPFunction.apply(ps, tgt, T, self.max_iterations, self.tolerance,
+                                                       getattr(self, "svd_literal", False), self.check_every)
         if self.verbose:
-            print("ICP converged in {} iterations".format(ii))
-        ps, T = ps.to(out_dev), T.to(out_dev)
-        return (ps[0], T[0]) if single else (ps, T)
+            print("ICP converged")
+        pc, T_out = pc.to(out_dev), T_out.to(out_dev)
+        return (pc[0], T_out[0]) if single else (pc, T_out)

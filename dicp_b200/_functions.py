@@ -156,6 +156,62 @@ class KabschSums(torch.autograd.Function):
         return gx, gy, None
 
 
+class KabschICPFunction(torch.autograd.Function):
+    """The whole Kabsch / SVD point-to-point loop (ICP.py:533-591) as one autograd node: nearest-neighbour search,
+    fused centroid / cross-covariance sums, 3x3 SVD + determinant fix + composition and the convergence test run as
+    kernels (`dicp_kabsch_icp_forward_*`), and so does the reverse pass (`dicp_kabsch_icp_backward_*`).
+    forward(source (N,n,3), target (N,m,S), T_init (N,4,4), max_iterations, tolerance, literal, check_every)
+      -> pc (N,n,3), T (N,4,4), iterations run (python int, non-differentiable)."""
+
+    @staticmethod
+    def forward(ctx, source, target, T_init, max_iterations, tolerance, literal, check_every):
+        require_cuda()
+        lib = load_library()
+        dev, dt = source.device, source.dtype
+        source, target, T_init = source.contiguous(), target.contiguous(), T_init.contiguous()
+        N, n, _ = source.shape
+        m, S = target.shape[1], target.shape[2]
+        K = int(max_iterations)
+        sfx = suffix(dt)
+        pc = torch.empty((N, n, 3), dtype=dt, device=dev)
+        T = torch.empty((N, 4, 4), dtype=dt, device=dev)
+        saved_idx = torch.empty((K, N, n), dtype=torch.int32, device=dev)
+        saved_state = torch.empty((K + 1, N, _lib.STATE_STRIDE), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.dicp_kabsch_icp_workspace_bytes(N, n, m, source.element_size()), dev)
+        iters = ctypes.c_int32(0)
+        with torch.cuda.device(dev):
+            rc = getattr(lib, "dicp_kabsch_icp_forward_" + sfx)(
+                ptr(source), ptr(target), ptr(T_init), N, n, m, S, K, float(tolerance), int(bool(literal)), int(check_every),
+                ptr(pc), ptr(T), ptr(saved_idx), ptr(saved_state), ctypes.byref(iters), ptr(ws), ws.numel(), stream_ptr(dev))
+        check(rc, "dicp_kabsch_icp_forward_" + sfx)
+        ctx.k_run = int(iters.value)
+        ctx.literal = int(bool(literal))
+        ctx.dims = (N, n, m, S)
+        ctx.ws = ws
+        ctx.save_for_backward(source, target, T_init, saved_idx, saved_state)
+        ctx.iterations = ctx.k_run
+        return pc, T
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_pc, g_T):
+        lib = load_library()
+        source, target, T_init, saved_idx, saved_state = ctx.saved_tensors
+        N, n, m, S = ctx.dims
+        dev, dt = source.device, source.dtype
+        sfx = suffix(dt)
+        g_pc = g_pc.contiguous() if g_pc is not None else None
+        g_T = g_T.contiguous() if g_T is not None else None
+        g_src, g_tgt = torch.empty_like(source), torch.empty_like(target)
+        g_T0 = torch.empty((N, 4, 4), dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            rc = getattr(lib, "dicp_kabsch_icp_backward_" + sfx)(
+                ptr(source), ptr(target), ptr(T_init), N, n, m, S, ctx.literal, ctx.k_run, ptr(saved_idx), ptr(saved_state),
+                ptr(g_T), ptr(g_pc), ptr(g_src), ptr(g_tgt), ptr(g_T0), ptr(ctx.ws), ctx.ws.numel(), stream_ptr(dev))
+        check(rc, "dicp_kabsch_icp_backward_" + sfx)
+        return g_src, g_tgt, g_T0, None, None, None, None
+
+
 def make_params(icp_type, dim, differentiable, loss_name, loss_metric, trim_dist, tanh_steepness, tolerance,
                 max_iterations, const_iter, match_ratio_thresh, check_every=1, nn_search="brute"):
     if loss_name not in _lib.LOSS_IDS:
@@ -255,6 +311,7 @@ class ICPFunction(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_pc, g_T, *_unused):
         lib = load_library()
         source, target, w_init, saved_idx, saved_state = ctx.saved_tensors

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "dicp_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_nn_packed_bytes": ([_I, _I, _I], _Z),
     "dicp_kabsch_workspace_bytes": ([_I, _I], _Z),
+    "dicp_kabsch_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_nn_grid_workspace_bytes": ([_I, _I, _I, _I], _Z),
 }
 for _s in ("f32", "f64"):
@@ -61,6 +62,9 @@ for _s in ("f32", "f64"):
                                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_kabsch_sums_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_kabsch_sums_bwd_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I)
+    _SIGNATURES["dicp_kabsch_icp_forward_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _I, _D, _I, _I, _P, _P, _P, _P,
+                                                     ctypes.POINTER(ctypes.c_int32), _P, _Z, _P], _I)
+    _SIGNATURES["dicp_kabsch_icp_backward_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_gumbel_nn_" + _s] = ([_P, _P, _I, _I, _I, _I, _U64, _D, _D, _P, _P, _P], _I)
     _SIGNATURES["dicp_gumbel_nn_bwd_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _U64, _D, _D, _P, _P, _P, _P], _I)
     _SIGNATURES["dicp_gumbel_noise_" + _s] = ([_I, _I, _I, _U64, _D, _P, _P], _I)

@@ -242,9 +242,8 @@ DICP_API int dicp_solve_update_f64(const double* partials, int nblk, const doubl
 
 /* ---- Kabsch / SVD point-to-point step: the per-point half of dICP/ICP.py:557-563 ----------
  * sums[b] = ( sum_i p_i (3), sum_i q_i (3), sum_i q_i p_i^T (9, row-major), pad ),  q_i = tgt[b, idx[b,i], :3]
- * from which the centroids and the cross-covariance W = M/n - q_mean p_mean^T follow; the 3x3
- * SVD, determinant fix and composition (ICP.py:566-578) are O(1) per pair and stay on the host
- * side (torch).  The _bwd entry is the adjoint used by autograd: grad_source is overwritten,
+ * from which the centroids and the cross-covariance W = M/n - q_mean p_mean^T follow (stage API of the
+ * loop below, exported for tests and profiling).  The _bwd entry is the adjoint used by autograd: grad_source is overwritten,
  * grad_target is zeroed and scatter-added into.                                              */
 DICP_API size_t dicp_kabsch_workspace_bytes(int N, int n);
 DICP_API int dicp_kabsch_sums_f32(const float* source, const float* target, const int32_t* idx, int N, int n, int m, int S,
@@ -255,6 +254,31 @@ DICP_API int dicp_kabsch_sums_bwd_f32(const float* source, const float* target, 
                              const float* grad_sums, float* grad_source, float* grad_target, void* stream);
 DICP_API int dicp_kabsch_sums_bwd_f64(const double* source, const double* target, const int32_t* idx, int N, int n, int m, int S,
                              const double* grad_sums, double* grad_source, double* grad_target, void* stream);
+
+/* ---- the whole Kabsch / SVD point-to-point loop: replaces dICP/ICP.py:533-591 -------------------
+ * Per iteration: search, fused sums, per-pair 3x3 SVD (one-sided Jacobi, double) + determinant fix +
+ * composition, convergence test sum|C x + r - q|^2 < tolerance per pair (a batch stops when every pair
+ * is below it; tolerance <= 0: no test, max_iterations are run).  literal != 0: C = U D V as ICP.py:570
+ * writes it, else the Kabsch rotation U D V^T.  T_init is only composed into T_out (ICP.py:545-547).
+ * saved_idx [K,N,n] int32, saved_state [(K+1),N,DICP_STATE_STRIDE] doubles; *iters_run_host is written
+ * before return (one stream synchronisation at the end, plus one every check_every iterations when a
+ * tolerance is set).  The _backward entry is the hand-written reverse pass: grad_T / grad_pc may be NULL,
+ * grad_source, grad_target, grad_T_init are overwritten.                                              */
+DICP_API size_t dicp_kabsch_icp_workspace_bytes(int N, int n, int m, int elem_size);
+DICP_API int dicp_kabsch_icp_forward_f32(const float* source, const float* target, const float* T_init, int N, int n, int m, int S,
+                                int max_iterations, double tolerance, int literal, int check_every, float* pc, float* T_out,
+                                int32_t* saved_idx, double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_kabsch_icp_forward_f64(const double* source, const double* target, const double* T_init, int N, int n, int m, int S,
+                                int max_iterations, double tolerance, int literal, int check_every, double* pc, double* T_out,
+                                int32_t* saved_idx, double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_kabsch_icp_backward_f32(const float* source, const float* target, const float* T_init, int N, int n, int m, int S,
+                                 int literal, int iters_run, const int32_t* saved_idx, const double* saved_state,
+                                 const float* grad_T, const float* grad_pc, float* grad_source, float* grad_target,
+                                 float* grad_T_init, void* ws, size_t ws_bytes, void* stream);
+DICP_API int dicp_kabsch_icp_backward_f64(const double* source, const double* target, const double* T_init, int N, int n, int m, int S,
+                                 int literal, int iters_run, const int32_t* saved_idx, const double* saved_state,
+                                 const double* grad_T, const double* grad_pc, double* grad_source, double* grad_target,
+                                 double* grad_T_init, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Gumbel-softmax soft nearest neighbour: replaces dICP/nn.py:43-70 ----------------------
  * out[b,i,:] = sum_j softmax_j((-|x_i - y_j|^2 + G_ij) / tau) y[b,j,:],  G = -log(-log(U+eps)+eps)

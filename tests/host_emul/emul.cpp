@@ -232,4 +232,12 @@ extern "C" {
   }
 EMUL_FWD(f32, float)
 EMUL_FWD(f64, double)
+// Kabsch / SVD step (dicp_math.cuh: svd3, kabsch_step, kabsch_step_backward)
+__attribute__((visibility("default"))) void emul_kabsch_step(const double* sums, double n, int literal, double* rec) {
+  dicp::kabsch_step(sums, n, literal != 0, rec);
+}
+__attribute__((visibility("default"))) void emul_kabsch_step_backward(const double* rec, double n, int literal, const double* Cbar,
+                                                                      const double* rbar, double* g) {
+  dicp::kabsch_step_backward(rec, n, literal != 0, Cbar, rbar, g);
+}
 }

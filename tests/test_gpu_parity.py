@@ -1,5 +1,7 @@
 """GPU parity tests: the CUDA path, called through the public API and the C ABI, against the
 oracle (oracle/) and the golden vectors of the unmodified reference (tests/golden/)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -8,6 +10,7 @@ from cases import DENSE_CASES, FIXTURE_CASES, golden_loss
 from helpers import load_golden, rel_err, se3_log, T_ts_true, tt
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 EPS32 = float(np.finfo(np.float32).eps)
 
@@ -499,6 +502,47 @@ def test_kabsch_3d_vs_oracle_with_gradients(dtype, tol):
         assert rel_err(ps[b].detach().cpu(), ps_r.detach()) < tol
         assert rel_err(s.grad[b].cpu(), sr.grad) < 50 * tol
         assert rel_err(t.grad[b].cpu(), tr.grad) < 50 * tol
+
+
+def test_kabsch_svd_config_key(tmp_path):
+    """The optional YAML key functionality.svd (commented out upstream, config/dICP_config.yaml:15-16) routes `icp()` of a
+    pt2pt object through the Kabsch / SVD kernels.  (The reference's literal product U D V, ICP.py:570, depends on the sign
+    convention of the SVD routine, which LAPACK does not specify, so it has no parity target beyond V = V^T; the
+    `svd_literal` switch and its adjoint are checked against finite differences in tests/test_kabsch_math.py.)"""
+    import yaml
+    from dICP.ICP import ICP
+    g = load_golden("svd_fixture")
+    src, tgt = tt(g["source"]).cuda(), tt(g["target"]).cuda()
+    with open(os.path.join(ROOT, "config", "dICP_config.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["dICP"]["functionality"]["svd"] = True
+    path = tmp_path / "svd.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    icp2 = ICP(config_path=str(path), icp_type="pt2pt", max_iterations=50, tolerance=1e-20)
+    res = icp2.icp(src, tgt, torch.eye(4, dtype=src.dtype, device="cuda"))
+    assert res["T"].shape == (1, 4, 4) and rel_err(res["T"][0].cpu(), g["T"]) < 1e-10
+
+
+def test_kabsch_batch_stops_when_every_pair_is_below_the_tolerance():
+    """Noise-free clouds converge exactly; the device-side test ends the loop early and T_init is only composed (ICP.py:545-547)."""
+    from dICP.ICP import ICP
+    from dicp_b200 import _functions
+    from oracle.dicp_oracle import kabsch_icp
+    gen = torch.Generator().manual_seed(3)
+    tgt = torch.rand((3, 500, 3), generator=gen, dtype=torch.float64) * 10.0
+    ang = 0.05
+    R = torch.tensor([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    src = tgt[:, :400] @ R.T + torch.tensor([0.02, -0.01, 0.03], dtype=torch.float64)
+    T0 = torch.eye(4, dtype=torch.float64).repeat(3, 1, 1)
+    T0[:, 0, 3] = torch.tensor([0.5, 0.0, -1.0], dtype=torch.float64)
+    ps, T = _functions.KabschICPFunction.apply(src.cuda(), tgt.cuda(), T0.cuda(), 40, 1e-18, False, 1)
+    iters = T.grad_fn.iterations if T.grad_fn is not None else None
+    worst = 0
+    for b in range(3):
+        ps_r, T_r, it = kabsch_icp(src[b], tgt[b], T0[b], 40, 1e-18)
+        worst = max(worst, it)
+        assert rel_err(T[b].cpu(), T_r) < 1e-10 and rel_err(ps[b].cpu(), ps_r) < 1e-10
+    assert worst < 40
 
 
 def test_kabsch_sums_stage_vs_torch():
