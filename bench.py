@@ -304,7 +304,7 @@ def roofline_bwd(src, tgt, pk, with_weight):
     st = _lib.stream_ptr(dev)
 
     def launch(k):
-        _lib.check(lib.dicp_icp_backward_f32(_lib.ptr(source), _lib.ptr(target), _lib.ptr(w_init) if with_weight else None, N, n, m, 6,
+        _lib.check(lib.dicp_icp_backward_f32(_lib.ptr(source), _lib.ptr(target), _lib.ptr(w_init) if with_weight else None, None, N, n, m, 6,
                                              ctypes.byref(p), k, _lib.ptr(saved_idx), _lib.ptr(saved_state), _lib.ptr(g_T), None,
                                              _lib.ptr(g_src), _lib.ptr(g_tgt), _lib.ptr(g_w), _lib.ptr(g_T0), _lib.ptr(ctx.ws), ctx.ws.numel(), st), "bwd")
 

@@ -118,6 +118,12 @@ class ICP:
         m_valid = None
         if isinstance(target, list) and len(target) > 0 and not _is_empty(source):
             m_valid = [max(len(t_i), 1) for t_i in target]
+        # ragged source lists: the real length of every cloud, so that the kernels neither search nor evaluate the zero
+        # padding (ICP.py:361-426 gives it weight 0, which is what skipping it amounts to; with a negative
+        # matched_ratio_thresh zero-weight rows would count as matched, so then the padding is processed as upstream)
+        n_valid = None
+        if isinstance(source, list) and len(source) > 0 and not _is_empty(target) and self.match_ratio_thresh >= 0.0:
+            n_valid = [max(len(s_i), 1) for s_i in source]
         default_prior = (weight is None and not self.source_zeroes_are_pad and not isinstance(source, list)
                          and not isinstance(target, list) and not _is_empty(source) and not _is_empty(target))
         source, target, T_init, w_init = self.batch_size_handling(source, target, T_init, weight)
@@ -162,6 +168,10 @@ class ICP:
             m_valid = None                                   # nothing is padded
         if m_valid is not None:
             m_valid = torch.tensor(m_valid, dtype=torch.int32, device=dev)
+        if n_valid is not None and (len(n_valid) != N or min(n_valid) == n):
+            n_valid = None                                   # nothing is padded
+        if n_valid is not None:
+            n_valid = torch.tensor(n_valid, dtype=torch.int32, device=dev)
         # host buffers are staged through the GPU; from pinned memory the copies are asynchronous and
         # stream-ordered in front of the kernels
         source_d, target_d = source.to(dev, non_blocking=True), target.to(dev, non_blocking=True)
@@ -172,7 +182,7 @@ class ICP:
         keep = [] if self.keep_correspondences else None
         pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
             source_d, target_d, T_init.to(dev, non_blocking=True),
-            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook, keep)
+            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook, keep, n_valid)
         if keep is not None:
             self.last_correspondences = keep[0]
 
@@ -246,9 +256,8 @@ class ICP:
                     prior = 0.0 * prior
                 clouds.append(s_i[:, :3])
                 priors.append(prior)
-            n_max = max(c.shape[0] for c in clouds)
-            source_batch = torch.stack([self._pad_rows(c, n_max, 0.0) for c in clouds], dim=0)
-            w = torch.stack([self._pad_rows(p_.unsqueeze(-1), n_max, 0.0).squeeze(-1) for p_ in priors], dim=0)
+            source_batch = self._stack_ragged(clouds, 0.0)
+            w = self._stack_ragged([p_.unsqueeze(-1) for p_ in priors], 0.0).squeeze(-1)
         elif source.dim() == 2 and source.shape[1] in (3, 6):
             source_batch = source[:, :3].unsqueeze(0)
             w = torch.ones((1, source_batch.shape[1]), dtype=dt, device=dev) if weight is None else weight.unsqueeze(0)
@@ -272,8 +281,7 @@ class ICP:
                 if i > 0 and (t_i.dim() != 2 or t_i.shape[1] != tcols):
                     raise ValueError("target list must contain (m x 3/6) tensors. All tensors must have same number of columns")
                 clouds.append(t_i)
-            m_max = max(c.shape[0] for c in clouds)
-            target_batch = torch.stack([self._pad_rows(c, m_max, pad_value) for c in clouds], dim=0)
+            target_batch = self._stack_ragged(clouds, pad_value)
             if dead:
                 alive = torch.ones((w.shape[0], 1), dtype=w.dtype, device=w.device)
                 alive[dead] = 0.0
@@ -302,13 +310,15 @@ class ICP:
         return source_batch, target_batch, T_batch, w
 
     @staticmethod
-    def _pad_rows(x, rows, value):
-        """(k,c) -> (rows,c), new rows filled with `value` (a float or a 0-d tensor)."""
-        short = rows - x.shape[0]
-        if short <= 0:
-            return x
-        fill = value * torch.ones((short, x.shape[1]), dtype=x.dtype, device=x.device)
-        return torch.cat((x, fill), dim=0)
+    def _stack_ragged(clouds, value):
+        """list of (k_i,c) -> (N, max k_i, c): ONE allocation filled with `value` (a float or a 0-d tensor) and one slice copy
+        per cloud, instead of the reference's incremental vstack / hstack of padded copies (ICP.py:361-426, 451-482)."""
+        rows = max(c.shape[0] for c in clouds)
+        first = clouds[0]
+        out = (value * torch.ones((len(clouds), rows, first.shape[1]), dtype=first.dtype, device=first.device))
+        for i, c in enumerate(clouds):
+            out[i, :c.shape[0]] = c
+        return out
 
     # ---------------------------------------------------------------------------------
     def pt2pt_dICP_SVD(self, source, target, T_init, trim_dist=None, huber_delta=None, dim=3):

@@ -244,13 +244,14 @@ class ICPFunction(torch.autograd.Function):
       -> pc, T (differentiable) and deltas, weights, costs, converged, num_iters, match_ratio
          (detached / non-differentiable, ICP.py:220-229, 288-292).
     m_valid (N,) int32 or None: real row count of every target cloud of a ragged batch.
+    n_valid (N,) int32 or None: real row count of every source cloud of a ragged batch (rows beyond it: padding).
     nn_hook: None, or a callable `nn_hook(k, state_k, idx_k)` that replaces the loop's own
       correspondence search (include/dicp_b200.h: dicp_icp_forward_hooked_*): `state_k` is the
       (N, 64) float64 record tensor of iteration k (pass it to `dicp_nn_scan_*`), `idx_k` the
       (N, n) int32 tensor to fill, both views of this call's saved buffers, on the current stream."""
 
     @staticmethod
-    def forward(ctx, source, target, T_init, w_init, params, m_valid=None, nn_hook=None, keep_idx=None):
+    def forward(ctx, source, target, T_init, w_init, params, m_valid=None, nn_hook=None, keep_idx=None, n_valid=None):
         require_cuda()
         lib = load_library()
         dev, dt = source.device, source.dtype
@@ -275,7 +276,7 @@ class ICPFunction(torch.autograd.Function):
         saved_state = torch.empty((K + 1, N, _lib.STATE_STRIDE), dtype=torch.float64, device=dev)
         ws = _workspace(lib.dicp_icp_workspace_bytes(N, n, m, source.element_size()), dev)
         iters = ctypes.c_int32(0)
-        args = (ptr(source), ptr(target), ptr(T_init), ptr(w_init), ptr(m_valid), N, n, m, S, ctypes.byref(params),
+        args = (ptr(source), ptr(target), ptr(T_init), ptr(w_init), ptr(m_valid), ptr(n_valid), N, n, m, S, ctypes.byref(params),
                 ptr(pc), ptr(T), ptr(deltas), ptr(weights), ptr(costs), ptr(converged), ptr(num_iters), ptr(match_ratio),
                 ptr(saved_idx), ptr(saved_state), ctypes.byref(iters), ptr(ws), ws.numel(), stream_ptr(dev))
         with torch.cuda.device(dev):
@@ -301,6 +302,7 @@ class ICPFunction(torch.autograd.Function):
         ctx.k_run = k_run
         ctx.dims = (N, n, m, S)
         ctx.has_w = w_init is not None
+        ctx.n_valid = n_valid
         ctx.save_for_backward(source, target, w_init if w_init is not None else source.new_empty(0),
                               saved_idx, saved_state)
         ctx.ws = ws
@@ -327,8 +329,8 @@ class ICPFunction(torch.autograd.Function):
         ws = ctx.ws
         with torch.cuda.device(dev):
             rc = getattr(lib, "dicp_icp_backward_" + sfx)(
-                ptr(source), ptr(target), ptr(w_init) if ctx.has_w else None, N, n, m, S, ctypes.byref(ctx.params), ctx.k_run,
+                ptr(source), ptr(target), ptr(w_init) if ctx.has_w else None, ptr(ctx.n_valid), N, n, m, S, ctypes.byref(ctx.params), ctx.k_run,
                 ptr(saved_idx), ptr(saved_state), ptr(g_T), ptr(g_pc), ptr(g_src), ptr(g_tgt), ptr(g_w), ptr(g_T0),
                 ptr(ws), ws.numel(), stream_ptr(dev))
         check(rc, "dicp_icp_backward_" + sfx)
-        return g_src, g_tgt, g_T0, g_w, None, None, None, None
+        return g_src, g_tgt, g_T0, g_w, None, None, None, None, None

@@ -54,11 +54,11 @@ for _s in ("f32", "f64"):
     _SIGNATURES["dicp_nn_scan_" + _s] = ([_P, _P, _P, _I, _I, _I, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_gather_rows_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)
     _SIGNATURES["dicp_gather_rows_bwd_" + _s] = ([_P, _P, _I, _I, _I, _I, _P, _P], _I)
-    _SIGNATURES["dicp_icp_forward_" + _s] = ([_P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams),
+    _SIGNATURES["dicp_icp_forward_" + _s] = ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams),
                                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                              ctypes.POINTER(ctypes.c_int32), _P, _Z, _P], _I)
     _SIGNATURES["dicp_icp_forward_hooked_" + _s] = (_SIGNATURES["dicp_icp_forward_" + _s][0] + [NN_HOOK, _P], _I)
-    _SIGNATURES["dicp_icp_backward_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams), _I,
+    _SIGNATURES["dicp_icp_backward_" + _s] = ([_P, _P, _P, _P, _I, _I, _I, _I, ctypes.POINTER(DicpParams), _I,
                                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_kabsch_sums_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P], _I)
     _SIGNATURES["dicp_kabsch_sums_bwd_" + _s] = ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I)

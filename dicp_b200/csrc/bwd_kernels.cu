@@ -74,7 +74,7 @@ __device__ __forceinline__ void bw_block_reduce_store(const T* vals, double* out
 template <typename T>
 __global__ void __launch_bounds__(BW_THREADS)
 bwd_seed_kernel(const T* __restrict__ source, const T* __restrict__ grad_pc, const double* __restrict__ state_final, int n,
-                T* __restrict__ grad_source, double* __restrict__ partials) {
+                T* __restrict__ grad_source, double* __restrict__ partials, const int32_t* __restrict__ n_valid) {
   __shared__ double red_smem[(BW_THREADS / 32) * BW_NRED];
   const int b = blockIdx.y;
   const double* rec = state_final + (size_t)b * ST_STRIDE;
@@ -92,7 +92,9 @@ bwd_seed_kernel(const T* __restrict__ source, const T* __restrict__ grad_pc, con
       const T* gp = grad_pc + ((size_t)b * n + i) * 3;
       g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
     }
-    const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
+    // padding rows of a ragged batch (i >= n_valid[b]) are zero points whatever the buffer holds
+    const bool real = n_valid == nullptr || i < n_valid[b];
+    const T p[3] = {real ? src_b[3 * i] : T(0), real ? src_b[3 * i + 1] : T(0), real ? src_b[3 * i + 2] : T(0)};
 #pragma unroll
     for (int c = 0; c < 3; ++c) gs_b[3 * i + c] = C[c] * g[0] + C[3 + c] * g[1] + C[6 + c] * g[2];
 #pragma unroll
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(BW_THREADS, BW_MINB)
 bwd_points_staged_kernel(const float* __restrict__ source, const void* __restrict__ rows, const float* __restrict__ w_init,
                          const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
                          int n, int m, WeightParams P, float* __restrict__ grad_source, float* __restrict__ gtab,
-                         float* __restrict__ grad_w, double* __restrict__ partials, int nrows, TilePlan plan, int gS) {
+                         float* __restrict__ grad_w, double* __restrict__ partials, int nrows, TilePlan plan, int gS,
+                         const int32_t* __restrict__ n_valid) {
   constexpr int U = BW_U, TILE = BW_TILE, STAGES = BW_STAGES, WARPS = BW_THREADS / 32;
   static_assert(STAGES >= 3, "a stage is refilled one step after its release");
   extern __shared__ __align__(128) unsigned char bw_smem[];
@@ -235,6 +238,11 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
 
   typedef TileCursor Cursor;
   auto tile_count = [&](const Cursor& c) { return min(TILE, n - c.j * TILE); };
+  // real correspondences of the tile: rows >= n_valid[b] of a ragged batch are padding, nothing flows into them
+  auto tile_valid = [&](const Cursor& c) {
+    const int nb = n_valid != nullptr ? min(n_valid[c.b], n) : n;
+    return max(0, min(TILE, nb - c.j * TILE));
+  };
   auto issue = [&](const Cursor& c) {
     const int s = c.L % STAGES;
     const uint32_t cnt = (uint32_t)tile_count(c);
@@ -259,7 +267,7 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
   struct Gathered { float q[U][3], nr[U][3]; int jj[U]; };
   auto gather = [&](const Cursor& c, Gathered& g) {
     const int s = c.L % STAGES;
-    const int cnt = tile_count(c);
+    const int cnt = tile_valid(c);
     mbar_wait(&full[s], (uint32_t)((c.L / STAGES) & 1));
     const size_t row_b = (size_t)c.b * m;
 #pragma unroll
@@ -301,7 +309,7 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
     if (cc.seg_first) enter(cc);
     last_tile = cc.tile(plan);
     const int s = cc.L % STAGES;
-    const int cnt = tile_count(cc);
+    const int cnt = tile_valid(cc);
     // this lane's staged inputs
     float p[U][3], gs[U][3], w0[U], gw[U];
 #pragma unroll
@@ -394,7 +402,8 @@ __global__ void __launch_bounds__(BW_THREADS)
 bwd_points_generic_kernel(const T* __restrict__ source, const T* __restrict__ target, const T* __restrict__ w_init,
                           const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
                           int n, int m, int S, WeightParams P, T* __restrict__ grad_source, T* __restrict__ grad_target,
-                          T* __restrict__ grad_w, double* __restrict__ partials, int nrows, TilePlan plan) {
+                          T* __restrict__ grad_w, double* __restrict__ partials, int nrows, TilePlan plan,
+                          const int32_t* __restrict__ n_valid) {
   __shared__ double red_smem[(BW_THREADS / 32) * 32];
   TileWalk walk;
   walk.init(plan, blockIdx.x);
@@ -430,7 +439,7 @@ bwd_points_generic_kernel(const T* __restrict__ source, const T* __restrict__ ta
     const T* tgt_b = target + (size_t)b * m * S;
     T* gt_b = grad_target + (size_t)b * m * S;
     T* gs_b = grad_source + (size_t)b * n * 3;
-    const int i0 = c.j * plan.tile, i_end = min(i0 + plan.tile, n);
+    const int i0 = c.j * plan.tile, i_end = min(i0 + plan.tile, n_valid != nullptr ? min(n_valid[b], n) : n);
     for (int i = i0 + threadIdx.x; i < i_end; i += BW_THREADS) {
       const int j = idx[(size_t)b * n + i];
       const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
@@ -483,7 +492,7 @@ bwd_unpack_gtab_kernel(const float* __restrict__ gtab, size_t total, int S, floa
 }
 
 template <typename T>
-static int icp_backward_impl(const T* source, const T* target, const T* w_init, int N, int n, int m, int S, const dicp_params* p,
+static int icp_backward_impl(const T* source, const T* target, const T* w_init, const int32_t* n_valid, int N, int n, int m, int S, const dicp_params* p,
                              int iters_run, const int32_t* saved_idx, const double* saved_state, const T* grad_T, const T* grad_pc,
                              T* grad_source, T* grad_target, T* grad_w, T* grad_T_init, void* ws, size_t ws_bytes, void* stream) {
   DICP_CHECK_ARG(source && target && p && saved_idx && saved_state && grad_source && grad_target && grad_T_init, "null pointer");
@@ -518,7 +527,7 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
     DICP_CUDA(cudaMemsetAsync(grad_target, 0, (size_t)N * m * S * sizeof(T), st));
   }
   if (grad_w != nullptr) DICP_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)N * n * sizeof(T), st));
-  bwd_seed_kernel<T><<<dim3(nseed, N), BW_THREADS, 0, st>>>(source, grad_pc, saved_state + (size_t)iters_run * rec_stride, n, grad_source, w.bw_partials);
+  bwd_seed_kernel<T><<<dim3(nseed, N), BW_THREADS, 0, st>>>(source, grad_pc, saved_state + (size_t)iters_run * rec_stride, n, grad_source, w.bw_partials, n_valid);
   DICP_LAUNCH_CHECK();
   constexpr size_t smem = (size_t)BW_STAGES * BW_STAGE_BYTES + (BW_THREADS / 32) * 64 * sizeof(double) + 2 * BW_STAGES * sizeof(uint64_t);
   for (int k = iters_run - 1; k >= 0; --k) {
@@ -539,7 +548,7 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
       attr_set = true;                                                                                                             \
     }                                                                                                                              \
     bwd_points_staged_kernel<PL, FW><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
-                                                                         grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w, w.bw_partials, nrows, plan, S); \
+                                                                         grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w, w.bw_partials, nrows, plan, S, n_valid); \
   } while (0)
         if (pl && fast) DICP_BW_LAUNCH(true, true);
         else if (pl) DICP_BW_LAUNCH(true, false);
@@ -550,7 +559,7 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
     } else {
 #define DICP_BW_LAUNCH(PL, FW)                                                                                                     \
   bwd_points_generic_kernel<T, PL, FW><<<plan.ctas, BW_THREADS, 0, st>>>(source, target, w_init, idx_k, rec_k, w.bw_state, n, m, S, P, \
-                                                                        grad_source, grad_target, grad_w, w.bw_partials, nrows, plan)
+                                                                        grad_source, grad_target, grad_w, w.bw_partials, nrows, plan, n_valid)
       if (pl && fast) DICP_BW_LAUNCH(true, true);
       else if (pl) DICP_BW_LAUNCH(true, false);
       else if (fast) DICP_BW_LAUNCH(false, true);
@@ -576,18 +585,18 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
 }  // namespace dicp
 
 extern "C" {
-int dicp_icp_backward_f32(const float* source, const float* target, const float* w_init, int N, int n, int m, int S,
+int dicp_icp_backward_f32(const float* source, const float* target, const float* w_init, const int32_t* n_valid, int N, int n, int m, int S,
                           const dicp_params* params, int iters_run, const int32_t* saved_idx, const double* saved_state,
                           const float* grad_T, const float* grad_pc, float* grad_source, float* grad_target, float* grad_w,
                           float* grad_T_init, void* ws, size_t ws_bytes, void* stream) {
-  return dicp::icp_backward_impl<float>(source, target, w_init, N, n, m, S, params, iters_run, saved_idx, saved_state, grad_T, grad_pc,
+  return dicp::icp_backward_impl<float>(source, target, w_init, n_valid, N, n, m, S, params, iters_run, saved_idx, saved_state, grad_T, grad_pc,
                                         grad_source, grad_target, grad_w, grad_T_init, ws, ws_bytes, stream);
 }
-int dicp_icp_backward_f64(const double* source, const double* target, const double* w_init, int N, int n, int m, int S,
+int dicp_icp_backward_f64(const double* source, const double* target, const double* w_init, const int32_t* n_valid, int N, int n, int m, int S,
                           const dicp_params* params, int iters_run, const int32_t* saved_idx, const double* saved_state,
                           const double* grad_T, const double* grad_pc, double* grad_source, double* grad_target, double* grad_w,
                           double* grad_T_init, void* ws, size_t ws_bytes, void* stream) {
-  return dicp::icp_backward_impl<double>(source, target, w_init, N, n, m, S, params, iters_run, saved_idx, saved_state, grad_T, grad_pc,
+  return dicp::icp_backward_impl<double>(source, target, w_init, n_valid, N, n, m, S, params, iters_run, saved_idx, saved_state, grad_T, grad_pc,
                                          grad_source, grad_target, grad_w, grad_T_init, ws, ws_bytes, stream);
 }
 }

@@ -164,7 +164,8 @@ int nn_pack_targets(const T* tgt, int N, int m, int S, const int32_t* m_valid, t
 // records [N, ST_STRIDE] whose C,r transform the queries first (ICP.py:137).
 template <typename T>
 int nn_search(const T* q, const double* state, const typename Vec4<T>::type* packed, int N, int n, int m,
-              int32_t* idx_out, T* d2_out, const int* stop_flag, void* ws, size_t ws_bytes, cudaStream_t st);
+              int32_t* idx_out, T* d2_out, const int* stop_flag, void* ws, size_t ws_bytes, cudaStream_t st,
+              const int32_t* n_valid = nullptr);   // n_valid [N] or NULL: real query count per pair; rows beyond it are padding
 size_t nn_search_ws_bytes(int N, int n, int m, int elem_size);
 
 // ---- uniform-grid exact NN (grid_nn_kernels.cu) ---------------------------------------
@@ -203,7 +204,7 @@ template <typename T> int gn_pack_rows(const T* target, int N, int m, int S, boo
 template <typename T>
 int gn_accumulate(const T* source, const T* target, const void* rows, const T* w_init, const int32_t* idx, StateView state,
                   int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,
-                  double* partials, const int* stop_flag, cudaStream_t st);
+                  double* partials, const int* stop_flag, cudaStream_t st, const int32_t* n_valid = nullptr);
 
 
 // ---- workspace of one forward / backward call (gn_kernels.cu) -------------------------

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(GN_THREADS, GN_MINB)
 gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict__ target, const void* __restrict__ rows,
                        const float* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, WeightParams P,
                        float* __restrict__ weights_out, long long w_pair_stride, double* __restrict__ partials, TilePlan plan,
-                       const int* __restrict__ stop_flag, int N) {
+                       const int* __restrict__ stop_flag, int N, const int32_t* __restrict__ n_valid) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   constexpr int U = GN_U, TILE = GN_TILE, STAGES = GN_STAGES, R = PT2PL ? 1 : 3, WARPS = GN_THREADS / 32;
   static_assert(STAGES >= 3, "a stage is refilled one step after its release");
@@ -172,6 +172,11 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
   // Tile L of this CTA lives in ring stage L % STAGES, use number L / STAGES of that stage.
   typedef TileCursor Cursor;
   auto tile_count = [&](const Cursor& c) { return min(TILE, n - c.j * TILE); };
+  // correspondences of the tile that are real: rows >= n_valid[b] of a ragged batch are padding (never evaluated, weight 0)
+  auto tile_valid = [&](const Cursor& c) {
+    const int nb = n_valid != nullptr ? min(n_valid[c.b], n) : n;
+    return max(0, min(TILE, nb - c.j * TILE));
+  };
 
   // one lane feeds the ring
   auto issue = [&](const Cursor& c) {
@@ -195,7 +200,7 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
   // waits for the tile's streams, then issues the row gathers of this lane's U correspondences
   auto gather = [&](const Cursor& c, Gathered& g) {
     const int s = c.L % STAGES;
-    const int cnt = tile_count(c);
+    const int cnt = tile_valid(c);
     mbar_wait(&full[s], (uint32_t)((c.L / STAGES) & 1));
     const size_t row_b = (size_t)c.b * m;
     const bool last_pair = c.b == N - 1;                       // the very last row of the tensor must not be over-read
@@ -252,7 +257,7 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
   auto compute = [&](const Cursor& c, const Gathered& g, Staged& in) {
     const int b = c.b;
     const int i0 = c.j * TILE;
-    const int cnt = tile_count(c);
+    const int cnt = tile_valid(c), cnt_all = tile_count(c);
 #pragma unroll
     for (int u = 0; u < U; ++u) in.w0[u] *= ctx.active;                                           // ICP.py:257
     PointEval<float> ev[U];
@@ -268,20 +273,31 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
     }
     if (weights_out != nullptr) {                                                                 // ICP.py:222, 164-165
       float* wrow = weights_out + (size_t)b * w_pair_stride + (size_t)(i0 + tid * U) * R;
-      if (U == 4 && cnt == TILE && (reinterpret_cast<uintptr_t>(wrow) & 15) == 0) {
+      float wv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) wv[u] = tid * U + u < cnt ? ev[u].w : 0.0f;        // padding rows of a ragged batch carry weight 0
+      if (U == 4 && cnt_all == TILE && (reinterpret_cast<uintptr_t>(wrow) & 15) == 0) {
         if (R == 1) {
-          __stcs(reinterpret_cast<float4*>(wrow), make_float4(ev[0].w, ev[1 % U].w, ev[2 % U].w, ev[3 % U].w));
+          __stcs(reinterpret_cast<float4*>(wrow), make_float4(wv[0], wv[1 % U], wv[2 % U], wv[3 % U]));
         } else {
-          __stcs(reinterpret_cast<float4*>(wrow), make_float4(ev[0].w, ev[0].w, ev[0].w, ev[1 % U].w));
-          __stcs(reinterpret_cast<float4*>(wrow) + 1, make_float4(ev[1 % U].w, ev[1 % U].w, ev[2 % U].w, ev[2 % U].w));
-          __stcs(reinterpret_cast<float4*>(wrow) + 2, make_float4(ev[2 % U].w, ev[3 % U].w, ev[3 % U].w, ev[3 % U].w));
+          __stcs(reinterpret_cast<float4*>(wrow), make_float4(wv[0], wv[0], wv[0], wv[1 % U]));
+          __stcs(reinterpret_cast<float4*>(wrow) + 1, make_float4(wv[1 % U], wv[1 % U], wv[2 % U], wv[2 % U]));
+          __stcs(reinterpret_cast<float4*>(wrow) + 2, make_float4(wv[2 % U], wv[3 % U], wv[3 % U], wv[3 % U]));
+        }
+      } else if (U == 2 && cnt_all == TILE && (reinterpret_cast<uintptr_t>(wrow) & 7) == 0) {
+        if (R == 1) {
+          __stcs(reinterpret_cast<float2*>(wrow), make_float2(wv[0], wv[1 % U]));
+        } else {
+          __stcs(reinterpret_cast<float2*>(wrow), make_float2(wv[0], wv[0]));
+          __stcs(reinterpret_cast<float2*>(wrow) + 1, make_float2(wv[0], wv[1 % U]));
+          __stcs(reinterpret_cast<float2*>(wrow) + 2, make_float2(wv[1 % U], wv[1 % U]));
         }
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (tid * U + u >= cnt) continue;
+          if (tid * U + u >= cnt_all) continue;
 #pragma unroll
-          for (int k = 0; k < R; ++k) wrow[u * R + k] = ev[u].w;
+          for (int k = 0; k < R; ++k) wrow[u * R + k] = wv[u];
         }
       }
     }
@@ -371,7 +387,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_accum_generic_kernel(const T* __restrict__ source, const T* __restrict__ target, const void* __restrict__ rows,
                         const T* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, int S,
                         WeightParams P, T* __restrict__ weights_out, long long w_pair_stride, double* __restrict__ partials,
-                        TilePlan plan, const int* __restrict__ stop_flag) {
+                        TilePlan plan, const int* __restrict__ stop_flag, const int32_t* __restrict__ n_valid) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   __shared__ double red_smem[(GN_THREADS / 32) * 32];
   constexpr int R = PT2PL ? 1 : 3;
@@ -395,7 +411,12 @@ gn_accum_generic_kernel(const T* __restrict__ source, const T* __restrict__ targ
     last_tile = c.tile(plan);
     const T* src_b = source + (size_t)b * n * 3;
     const int32_t* idx_b = idx + (size_t)b * n;
-    const int i_end = min(i0 + plan.tile, n);
+    const int nb = n_valid != nullptr ? min(n_valid[b], n) : n;      // rows >= n_valid[b] are padding: weight 0, never evaluated
+    const int i_end = min(i0 + plan.tile, nb);
+    if (weights_out != nullptr) {
+      for (int i = max(i0, nb) + threadIdx.x; i < min(i0 + plan.tile, n); i += GN_THREADS)
+        for (int k = 0; k < R; ++k) weights_out[(size_t)b * w_pair_stride + (size_t)i * R + k] = T(0);
+    }
     for (int i = i0 + threadIdx.x; i < i_end; i += GN_THREADS) {
       const int j = idx_b[i];
       const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
@@ -452,7 +473,7 @@ template int gn_pack_rows<double>(const double*, int, int, int, bool, void*, cud
 template <typename T>
 int gn_accumulate(const T* source, const T* target, const void* rows, const T* w_init, const int32_t* idx, StateView state,
                   int N, int n, int m, int S, const dicp_params* p, T* weights_out, long long w_pair_stride,
-                  double* partials, const int* stop_flag, cudaStream_t st) {
+                  double* partials, const int* stop_flag, cudaStream_t st, const int32_t* n_valid) {
   const WeightParams P = make_weight_params(p);
   const TilePlan plan = gn_tile_plan(N, n);
   const bool pl = p->icp_type == DICP_PT2PL;
@@ -474,7 +495,7 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
     }                                                                                                                              \
     gn_accum_staged_kernel<PL, DM, FW><<<dim3(plan.ctas, 1, 1), GN_THREADS, smem, st>>>(                                            \
         source, target, (pl && rows24) ? nullptr : rows, w_init, idx, state, n, m, P, weights_out, w_pair_stride, partials, plan,  \
-        stop_flag, N);                                                                                                             \
+        stop_flag, N, n_valid);                                                                                                    \
   } while (0)
 #define DICP_GN_LAUNCH(PL, DM)             \
   do {                                     \
@@ -492,9 +513,9 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
 #define DICP_GN_LAUNCH(PL, DM)                                                                                                     \
   do {                                                                                                                             \
     if (fast) gn_accum_generic_kernel<T, PL, DM, true><<<plan.ctas, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P, \
-                                                                                       weights_out, w_pair_stride, partials, plan, stop_flag); \
+                                                                                       weights_out, w_pair_stride, partials, plan, stop_flag, n_valid); \
     else gn_accum_generic_kernel<T, PL, DM, false><<<plan.ctas, GN_THREADS, 0, st>>>(source, target, rows, w_init, idx, state, n, m, S, P, \
-                                                                                   weights_out, w_pair_stride, partials, plan, stop_flag); \
+                                                                                   weights_out, w_pair_stride, partials, plan, stop_flag, n_valid); \
   } while (0)
     if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
     else if (pl) DICP_GN_LAUNCH(true, 2);
@@ -506,9 +527,9 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
   return 0;
 }
 template int gn_accumulate<float>(const float*, const float*, const void*, const float*, const int32_t*, StateView, int, int, int, int,
-                                  const dicp_params*, float*, long long, double*, const int*, cudaStream_t);
+                                  const dicp_params*, float*, long long, double*, const int*, cudaStream_t, const int32_t*);
 template int gn_accumulate<double>(const double*, const double*, const void*, const double*, const int32_t*, StateView, int, int, int, int,
-                                   const dicp_params*, double*, long long, double*, const int*, cudaStream_t);
+                                   const dicp_params*, double*, long long, double*, const int*, cudaStream_t, const int32_t*);
 
 // sum the CTA partial rows of pair b in a fixed order (thread v sums slot v)
 __device__ __forceinline__ void sum_partials(const double* partials, int b, int nblk, int nslots, double* red) {
@@ -589,8 +610,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 finalize_kernel(const T* __restrict__ source, int n, const double* __restrict__ state_all, int N, const Ctrl* __restrict__ ctrl,
                 double thresh, double rows, T* __restrict__ pc, T* __restrict__ T_out,
-                T* __restrict__ num_iters, T* __restrict__ match_ratio) {
+                T* __restrict__ num_iters, T* __restrict__ match_ratio, const int32_t* __restrict__ n_valid) {
   const int b = blockIdx.y;
+  const int nb = n_valid != nullptr ? min(n_valid[b], n) : n;      // padding rows of a ragged batch are zero points: pc = r
   const int kr = ctrl->iters_run;
   const double* after = state_all + ((size_t)kr * N + b) * ST_STRIDE;
   T C[9], r[3];
@@ -601,9 +623,11 @@ finalize_kernel(const T* __restrict__ source, int n, const double* __restrict__ 
   const T* src_b = source + (size_t)b * n * 3;
   T* pc_b = pc + (size_t)b * n * 3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
-    T a[3];
-    rotate(C, p, a);
+    T a[3] = {T(0), T(0), T(0)};
+    if (i < nb) {
+      const T p[3] = {src_b[3 * i], src_b[3 * i + 1], src_b[3 * i + 2]};
+      rotate(C, p, a);
+    }
     pc_b[3 * i] = a[0] + r[0]; pc_b[3 * i + 1] = a[1] + r[1]; pc_b[3 * i + 2] = a[2] + r[2];   // ICP.py:274
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -645,7 +669,8 @@ IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int 
 }
 
 template <typename T>
-static int icp_forward_impl(const T* source, const T* target, const T* T_init, const T* w_init, const int32_t* m_valid, int N, int n,
+static int icp_forward_impl(const T* source, const T* target, const T* T_init, const T* w_init, const int32_t* m_valid,
+                            const int32_t* n_valid, int N, int n,
                             int m, int S, const dicp_params* p, T* pc, T* T_out, T* deltas, T* weights, T* costs, uint8_t* converged,
                             T* num_iters, T* match_ratio, int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
                             void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook = nullptr, void* hook_user = nullptr) {
@@ -711,10 +736,10 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
       rc = hook(hook_user, k, rec_k, idx_k);     // the caller's search (e.g. targets split over GPUs), stream-ordered
       if (rc) { set_error("dicp_icp_forward: the correspondence hook failed at iteration %d (code %d)", k, rc); return rc; }
     } else if (use_grid) rc = grid_search<T>(source, rec_k, N, n, m, gw, true, idx_k, nullptr, &w.ctrl->stop, st);
-    else rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st);
+    else rc = nn_search<T>(source, rec_k, (const V4*)w.packed, N, n, m, idx_k, nullptr, &w.ctrl->stop, w.nn_ws, w.nn_ws_bytes, st, n_valid);
     if (rc) return rc;
     rc = gn_accumulate<T>(source, target, rows, w_init, idx_k, state_view_records(rec_k), N, n, m, S, p,
-                          weights != nullptr ? weights + (size_t)k * nw : nullptr, (long long)K * nw, w.partials, &w.ctrl->stop, st);
+                          weights != nullptr ? weights + (size_t)k * nw : nullptr, (long long)K * nw, w.partials, &w.ctrl->stop, st, n_valid);
     if (rc) return rc;
     gn_update_kernel<T><<<N, 128, 0, st>>>(w.partials, nblk, rec_k, rec_k + rec_stride, k, p->dim, p->const_iter, p->tolerance,
                                            deltas, costs, weights, K, nw, converged, num_iters, match_ratio, w.ctrl, N);
@@ -727,7 +752,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   }
   dim3 fgrid((n + 2047) / 2048 < 128 ? (n + 2047) / 2048 : 128, N);
   finalize_kernel<T><<<fgrid, 256, 0, st>>>(source, n, saved_state, N, w.ctrl, p->match_ratio_thresh, (double)nw,
-                                            pc, T_out, num_iters, match_ratio);
+                                            pc, T_out, num_iters, match_ratio, n_valid);
   DICP_LAUNCH_CHECK();
   DICP_CUDA(cudaMemcpyAsync(&h, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   DICP_CUDA(cudaStreamSynchronize(st));
@@ -801,36 +826,36 @@ size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size) {
   return dicp::plan_workspace(nullptr, 0, N, n, m, elem_size).total;
 }
 
-int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init, const int32_t* m_valid,
+int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init, const int32_t* m_valid, const int32_t* n_valid,
                          int N, int n, int m, int S, const dicp_params* params, float* pc, float* T_out, float* deltas, float* weights, float* costs,
                          uint8_t* converged, float* num_iters, float* match_ratio, int32_t* saved_idx, double* saved_state,
                          int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream) {
-  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, m_valid, n_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                        converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
 }
-int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init, const int32_t* m_valid,
+int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init, const int32_t* m_valid, const int32_t* n_valid,
                          int N, int n, int m, int S, const dicp_params* params, double* pc, double* T_out, double* deltas, double* weights,
                          double* costs, uint8_t* converged, double* num_iters, double* match_ratio, int32_t* saved_idx,
                          double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream) {
-  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, n_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                         converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream);
 }
-int dicp_icp_forward_hooked_f32(const float* source, const float* target, const float* T_init, const float* w_init, const int32_t* m_valid,
+int dicp_icp_forward_hooked_f32(const float* source, const float* target, const float* T_init, const float* w_init, const int32_t* m_valid, const int32_t* n_valid,
                                 int N, int n, int m, int S, const dicp_params* params, float* pc, float* T_out, float* deltas, float* weights,
                                 float* costs, uint8_t* converged, float* num_iters, float* match_ratio, int32_t* saved_idx,
                                 double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook,
                                 void* user) {
   if (hook == nullptr) { dicp::set_error("dicp_icp_forward_hooked: null hook"); return DICP_ERR_ARG; }
-  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+  return dicp::icp_forward_impl<float>(source, target, T_init, w_init, m_valid, n_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                        converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream, hook, user);
 }
-int dicp_icp_forward_hooked_f64(const double* source, const double* target, const double* T_init, const double* w_init, const int32_t* m_valid,
+int dicp_icp_forward_hooked_f64(const double* source, const double* target, const double* T_init, const double* w_init, const int32_t* m_valid, const int32_t* n_valid,
                                 int N, int n, int m, int S, const dicp_params* params, double* pc, double* T_out, double* deltas, double* weights,
                                 double* costs, uint8_t* converged, double* num_iters, double* match_ratio, int32_t* saved_idx,
                                 double* saved_state, int32_t* iters_run_host, void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook,
                                 void* user) {
   if (hook == nullptr) { dicp::set_error("dicp_icp_forward_hooked: null hook"); return DICP_ERR_ARG; }
-  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
+  return dicp::icp_forward_impl<double>(source, target, T_init, w_init, m_valid, n_valid, N, n, m, S, params, pc, T_out, deltas, weights, costs,
                                         converged, num_iters, match_ratio, saved_idx, saved_state, iters_run_host, ws, ws_bytes, stream, hook, user);
 }
 int dicp_solve_update_f32(const double* partials, int nblk, const double* C_r, int N, const dicp_params* params, float* delta,

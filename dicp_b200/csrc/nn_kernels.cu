@@ -165,12 +165,25 @@ __global__ void __launch_bounds__(THREADS)
 nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
                const typename Vec4<T>::type* __restrict__ packed, int n, int m_pad, int tiles_per_split,
                int32_t* __restrict__ idx_out, T* __restrict__ d2_out, T* __restrict__ part_d2,
-               int32_t* __restrict__ part_idx, const int* __restrict__ stop_flag) {
+               int32_t* __restrict__ part_idx, const int* __restrict__ stop_flag, const int32_t* __restrict__ n_valid) {
   constexpr int NN_THREADS = THREADS;
   typedef typename Vec4<T>::type V4;
   if (stop_flag != nullptr && *stop_flag != 0) return;
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
+  // rows >= n_valid[b] of a ragged batch are padding: they get index 0 and cost nothing (a CTA of padding exits at once)
+  const int nb = n_valid != nullptr ? min(max(n_valid[b], 1), n) : n;
+  if (blockIdx.x * (NN_THREADS * Q) >= nb) {
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const int i = blockIdx.x * (NN_THREADS * Q) + tid + k * NN_THREADS;
+      if (i >= n) continue;
+      const size_t o = (size_t)b * n + i;
+      if (part_d2 == nullptr) { idx_out[o] = 0; if (d2_out != nullptr) d2_out[o] = T(0); }
+      else { part_d2[((size_t)blockIdx.z * gridDim.y) * n + o] = Sentinel<T>::inf(); part_idx[((size_t)blockIdx.z * gridDim.y) * n + o] = 0; }
+    }
+    return;
+  }
   __shared__ __align__(16) V4 tile[2][NN_TILE];
   const int split = blockIdx.z;
   const int N = gridDim.y;
@@ -191,7 +204,7 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
     int i = q0 + k * NN_THREADS;
-    if (i >= n) i = n - 1;
+    if (i >= nb) i = nb - 1;
     const T* p = q + ((size_t)b * n + i) * 3;
     T pv[3] = {p[0], p[1], p[2]};
     if (state != nullptr) {
@@ -251,6 +264,12 @@ nn_scan_kernel(const T* __restrict__ q, const double* __restrict__ state,
     const int i = q0 + k * NN_THREADS;
     if (i >= n) continue;
     int found = -1;
+    if (i >= nb) {                              // padding row inside a partly valid block
+      const size_t o = (size_t)b * n + i;
+      if (part_d2 == nullptr) { idx_out[o] = 0; if (d2_out != nullptr) d2_out[o] = T(0); }
+      else { part_d2[((size_t)split * N) * n + o] = Sentinel<T>::inf(); part_idx[((size_t)split * N) * n + o] = 0; }
+      continue;
+    }
     const V4* ch = tg + (size_t)bchunk[k] * NN_CHUNK;
     if (t_begin < t_end) {
 #pragma unroll 4
@@ -329,7 +348,7 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
                    int m_pad, int tiles_per_split, int32_t* __restrict__ idx_out, float* __restrict__ d2_out,
                    float* __restrict__ part_d2, int32_t* __restrict__ part_idx, unsigned int* __restrict__ fb_count,
                    int32_t* __restrict__ fb_list, float* __restrict__ fb_thr, int fb_cap, unsigned long long* __restrict__ fb_key,
-                   const int* __restrict__ stop_flag) {
+                   const int* __restrict__ stop_flag, const int32_t* __restrict__ n_valid) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
   __shared__ __align__(16) float4 tile[2][NNF_TILE];
   const float INF = Sentinel<float>::inf();
@@ -337,6 +356,19 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
   const int b = blockIdx.y;
   const int split = blockIdx.z;
   const int N = gridDim.y;
+  // rows >= n_valid[b] of a ragged batch are padding: they get index 0 and cost nothing (a CTA of padding exits at once)
+  const int nb = n_valid != nullptr ? min(max(n_valid[b], 1), n) : n;
+  if (blockIdx.x * (NNF_THREADS * Q) >= nb) {
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const int i = blockIdx.x * (NNF_THREADS * Q) + tid + k * NNF_THREADS;
+      if (i >= n) continue;
+      const size_t o = (size_t)b * n + i;
+      if (part_d2 == nullptr) { idx_out[o] = 0; if (d2_out != nullptr) d2_out[o] = 0.0f; }
+      else { part_d2[((size_t)split * N) * n + o] = INF; part_idx[((size_t)split * N) * n + o] = 0; }
+    }
+    return;
+  }
   const float4* tg = packed + (size_t)b * m_pad;
   const float4* tg_orig = nn_orig_records(packed, N, m_pad) + (size_t)b * m_pad;
   const float4 ctr = nn_centers(packed, N, m_pad)[b];
@@ -363,7 +395,7 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
     int i = q0 + k * NNF_THREADS;
-    if (i >= n) i = n - 1;
+    if (i >= nb) i = nb - 1;
     float xo[3];
     query_point(i, xo);
     x[k][0] = xo[0] - ctr.x; x[k][1] = xo[1] - ctr.y; x[k][2] = xo[2] - ctr.z;
@@ -483,6 +515,11 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
     const size_t o = (size_t)b * n + i;
     int found = 0;
     float bd = INF;
+    if (i >= nb) {                              // padding row inside a partly valid block
+      if (part_d2 == nullptr) { idx_out[o] = 0; if (d2_out != nullptr) d2_out[o] = 0.0f; }
+      else { part_d2[((size_t)split * N) * n + o] = INF; part_idx[((size_t)split * N) * n + o] = 0; }
+      continue;
+    }
     if (t_begin < t_end) {
       const float margin = nn_filter_margin(x[k][0], x[k][1], x[k][2], best[k]);
       if (!(second[k] - best[k] > margin)) {
@@ -749,19 +786,19 @@ static NNWorkspace nn_ws_layout(void* ws, size_t ws_bytes, int N, int n, int m, 
 size_t nn_search_ws_bytes(int N, int n, int m, int elem_size) { return nn_ws_layout(nullptr, 0, N, n, m, elem_size).total; }
 
 static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_t st, const float* q, const double* state, const float4* packed,
-                       int n, int m_pad, int32_t* idx_out, float* d2_out, const int* stop_flag) {
+                       int n, int m_pad, int32_t* idx_out, float* d2_out, const int* stop_flag, const int32_t* n_valid) {
   dim3 grid(p.gx, N, p.nsplit);
   DICP_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(unsigned int) * N, st));
   nn_scan_f32_kernel<8><<<grid, NNF_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out, (float*)w.part_d2,
-                                                         w.part_idx, w.fb_count, w.fb_list, w.fb_thr, w.fb_cap, w.fb_key, stop_flag);
+                                                         w.part_idx, w.fb_count, w.fb_list, w.fb_thr, w.fb_cap, w.fb_key, stop_flag, n_valid);
   DICP_LAUNCH_CHECK();
   return 0;
 }
 static int launch_scan(const NNPlan& p, const NNWorkspace& w, int N, cudaStream_t st, const double* q, const double* state, const double4* packed,
-                       int n, int m_pad, int32_t* idx_out, double* d2_out, const int* stop_flag) {
+                       int n, int m_pad, int32_t* idx_out, double* d2_out, const int* stop_flag, const int32_t* n_valid) {
   dim3 grid(p.gx, N, p.nsplit);
   nn_scan_kernel<double, 2, NN_THREADS><<<grid, NN_THREADS, 0, st>>>(q, state, packed, n, m_pad, p.tiles_per_split, idx_out, d2_out,
-                                                                     (double*)w.part_d2, w.part_idx, stop_flag);
+                                                                     (double*)w.part_d2, w.part_idx, stop_flag, n_valid);
   DICP_LAUNCH_CHECK();
   return 0;
 }
@@ -802,13 +839,13 @@ static int launch_fallback(const NNWorkspace&, int, cudaStream_t, const double*,
 
 template <typename T>
 int nn_search(const T* q, const double* state, const typename Vec4<T>::type* packed, int N, int n, int m,
-              int32_t* idx_out, T* d2_out, const int* stop_flag, void* ws, size_t ws_bytes, cudaStream_t st) {
+              int32_t* idx_out, T* d2_out, const int* stop_flag, void* ws, size_t ws_bytes, cudaStream_t st, const int32_t* n_valid) {
   if (N > 65535) { set_error("nn_search: N > 65535 pairs per call is not supported"); return DICP_ERR_ARG; }
   const NNPlan p = nn_plan(N, n, m, sizeof(T));
   const int m_pad = nn_m_pad(m);
   const NNWorkspace w = nn_ws_layout(ws, ws_bytes, N, n, m, sizeof(T));
   if (w.total > 0 && (ws == nullptr || w.total > ws_bytes)) { set_error("nn_search: workspace too small"); return DICP_ERR_WORKSPACE; }
-  int rc = launch_scan(p, w, N, st, q, state, packed, n, m_pad, idx_out, d2_out, stop_flag);
+  int rc = launch_scan(p, w, N, st, q, state, packed, n, m_pad, idx_out, d2_out, stop_flag, n_valid);
   if (rc) return rc;
   if (p.nsplit > 1) {
     const size_t total = (size_t)N * n;
@@ -817,8 +854,8 @@ int nn_search(const T* q, const double* state, const typename Vec4<T>::type* pac
   }
   return launch_fallback(w, N, st, q, state, packed, n, m_pad, idx_out, d2_out, stop_flag);
 }
-template int nn_search<float>(const float*, const double*, const float4*, int, int, int, int32_t*, float*, const int*, void*, size_t, cudaStream_t);
-template int nn_search<double>(const double*, const double*, const double4*, int, int, int, int32_t*, double*, const int*, void*, size_t, cudaStream_t);
+template int nn_search<float>(const float*, const double*, const float4*, int, int, int, int32_t*, float*, const int*, void*, size_t, cudaStream_t, const int32_t*);
+template int nn_search<double>(const double*, const double*, const double4*, int, int, int, int32_t*, double*, const int*, void*, size_t, cudaStream_t, const int32_t*);
 
 size_t nn_workspace_bytes(int N, int n, int m, int elem_size) {
   return nn_packed_bytes(N, m, elem_size) + nn_search_ws_bytes(N, n, m, elem_size);

@@ -146,6 +146,11 @@ DICP_API int dicp_gather_rows_bwd_f64(const double* grad_out, const int32_t* idx
  *         m_valid [N] int32 or NULL: number of real rows of every target cloud; rows beyond it
  *         are padding of a ragged batch (ICP.py:471-479) and are never returned as a neighbour,
  *         whatever they contain
+ *         n_valid [N] int32 or NULL: number of real rows of every source cloud; rows beyond it are
+ *         the zero padding of a ragged batch (ICP.py:361-426): they are never searched or evaluated
+ *         (a block of padding costs nothing), their `weights` rows are 0, their `pc` rows the bare
+ *         translation and nothing flows into them in the reverse pass -- what the reference obtains
+ *         by giving zero points a zero weight.  Pass the same array to the backward call.
  * outputs pc [N,n,3], T [N,4,4],
  *         deltas  [N,K,6]        K = max_iterations rows are allocated; the first
  *         weights [N,K,n*R]      *iters_run_host are valid (R = 1 pt2pl, 3 pt2pt)
@@ -157,13 +162,13 @@ DICP_API int dicp_gather_rows_bwd_f64(const double* grad_out, const int32_t* idx
  *         once at its end, and every check_every iterations when !const_iter).          */
 DICP_API size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size);
 DICP_API int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init,
-                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
+                         const int32_t* m_valid, const int32_t* n_valid, int N, int n, int m, int S, const dicp_params* params,
                          float* pc, float* T_out, float* deltas, float* weights, float* costs,
                          uint8_t* converged, float* num_iters, float* match_ratio,
                          int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
                          void* ws, size_t ws_bytes, void* stream);
 DICP_API int dicp_icp_forward_f64(const double* source, const double* target, const double* T_init, const double* w_init,
-                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
+                         const int32_t* m_valid, const int32_t* n_valid, int N, int n, int m, int S, const dicp_params* params,
                          double* pc, double* T_out, double* deltas, double* weights, double* costs,
                          uint8_t* converged, double* num_iters, double* match_ratio,
                          int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
@@ -179,13 +184,13 @@ DICP_API int dicp_icp_forward_f64(const double* source, const double* target, co
  * packed; everything else is identical to dicp_icp_forward_*.                              */
 typedef int (*dicp_nn_hook)(void* user, int iteration, const double* state_k, int32_t* idx_k);
 DICP_API int dicp_icp_forward_hooked_f32(const float* source, const float* target, const float* T_init, const float* w_init,
-                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
+                         const int32_t* m_valid, const int32_t* n_valid, int N, int n, int m, int S, const dicp_params* params,
                          float* pc, float* T_out, float* deltas, float* weights, float* costs,
                          uint8_t* converged, float* num_iters, float* match_ratio,
                          int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
                          void* ws, size_t ws_bytes, void* stream, dicp_nn_hook hook, void* user);
 DICP_API int dicp_icp_forward_hooked_f64(const double* source, const double* target, const double* T_init, const double* w_init,
-                         const int32_t* m_valid, int N, int n, int m, int S, const dicp_params* params,
+                         const int32_t* m_valid, const int32_t* n_valid, int N, int n, int m, int S, const dicp_params* params,
                          double* pc, double* T_out, double* deltas, double* weights, double* costs,
                          uint8_t* converged, double* num_iters, double* match_ratio,
                          int32_t* saved_idx, double* saved_state, int32_t* iters_run_host,
@@ -195,13 +200,13 @@ DICP_API int dicp_icp_forward_hooked_f64(const double* source, const double* tar
  * grad_T [N,4,4], grad_pc [N,n,3] (either may be NULL == zero)
  * grad_source [N,n,3], grad_target [N,m,S], grad_w [N,n] (may be NULL), grad_T_init [N,4,4]
  * are overwritten.  iters_run is the value the forward returned.                        */
-DICP_API int dicp_icp_backward_f32(const float* source, const float* target, const float* w_init,
+DICP_API int dicp_icp_backward_f32(const float* source, const float* target, const float* w_init, const int32_t* n_valid,
                           int N, int n, int m, int S, const dicp_params* params, int iters_run,
                           const int32_t* saved_idx, const double* saved_state,
                           const float* grad_T, const float* grad_pc,
                           float* grad_source, float* grad_target, float* grad_w, float* grad_T_init,
                           void* ws, size_t ws_bytes, void* stream);
-DICP_API int dicp_icp_backward_f64(const double* source, const double* target, const double* w_init,
+DICP_API int dicp_icp_backward_f64(const double* source, const double* target, const double* w_init, const int32_t* n_valid,
                           int N, int n, int m, int S, const dicp_params* params, int iters_run,
                           const int32_t* saved_idx, const double* saved_state,
                           const double* grad_T, const double* grad_pc,

@@ -50,7 +50,7 @@ def forward(source, target, T_init, w_init, params):
     iters = ctypes.c_int32(0)
     fn = getattr(lib, "emul_icp_forward_" + sfx)
     fn.restype = ctypes.c_int
-    rc = fn(_p(source), _p(target), _p(T_init), _p(w_init), None, N, n, m, S, ctypes.byref(params), _p(out["pc"]), _p(out["T"]),
+    rc = fn(_p(source), _p(target), _p(T_init), _p(w_init), None, None, N, n, m, S, ctypes.byref(params), _p(out["pc"]), _p(out["T"]),
             _p(out["deltas"]), _p(out["weights"]), _p(out["costs"]), _p(out["converged"]), _p(out["iterations"]),
             _p(out["matched_ratio"]), _p(out["saved_idx"]), _p(out["saved_state"]), ctypes.byref(iters), None,
             ctypes.c_size_t(0), None)
@@ -74,7 +74,7 @@ def backward(source, target, w_init, params, fwd, grad_T, grad_pc):
              w=torch.empty((N, n), dtype=dt) if w_init is not None else None, T_init=torch.empty((N, 4, 4), dtype=dt))
     fn = getattr(lib, "emul_icp_backward_" + sfx)
     fn.restype = ctypes.c_int
-    rc = fn(_p(source), _p(target), _p(w_init.contiguous()) if w_init is not None else None, N, n, m, S, ctypes.byref(params),
+    rc = fn(_p(source), _p(target), _p(w_init.contiguous()) if w_init is not None else None, None, N, n, m, S, ctypes.byref(params),
             fwd["k_run"], _p(fwd["saved_idx"]), _p(fwd["saved_state"]), _p(grad_T.contiguous()) if grad_T is not None else None,
             _p(grad_pc.contiguous()) if grad_pc is not None else None, _p(g["source"]), _p(g["target"]), _p(g["w"]), _p(g["T_init"]),
             None, ctypes.c_size_t(0), None)

@@ -216,7 +216,7 @@ static int backward(const T* source, const T* target, const T* w_init, int N, in
 extern "C" {
 #define EMUL_FWD(SFX, T)                                                                                                          \
   __attribute__((visibility("default"))) int emul_icp_forward_##SFX(                                                              \
-      const T* source, const T* target, const T* T_init, const T* w_init, const int32_t*, int N, int n, int m, int S,            \
+      const T* source, const T* target, const T* T_init, const T* w_init, const int32_t*, const int32_t*, int N, int n, int m, int S, \
       const dicp_params* p, T* pc,                                                                                               \
       T* T_out, T* deltas, T* weights, T* costs, uint8_t* converged, T* num_iters, T* match_ratio, int32_t* saved_idx,            \
       double* saved_state, int32_t* iters_run, void*, size_t, void*) {                                                            \
@@ -224,7 +224,7 @@ extern "C" {
                       match_ratio, saved_idx, saved_state, iters_run);                                                            \
   }                                                                                                                               \
   __attribute__((visibility("default"))) int emul_icp_backward_##SFX(                                                             \
-      const T* source, const T* target, const T* w_init, int N, int n, int m, int S, const dicp_params* p, int iters_run,         \
+      const T* source, const T* target, const T* w_init, const int32_t*, int N, int n, int m, int S, const dicp_params* p, int iters_run, \
       const int32_t* saved_idx, const double* saved_state, const T* grad_T, const T* grad_pc, T* g_src, T* g_tgt, T* g_w,         \
       T* g_T0, void*, size_t, void*) {                                                                                            \
     return backward<T>(source, target, w_init, N, n, m, S, p, iters_run, saved_idx, saved_state, grad_T, grad_pc, g_src, g_tgt,   \

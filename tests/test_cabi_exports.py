@@ -37,7 +37,7 @@ def test_version_and_arg_errors():
     rc = lib.dicp_nn_argmin_f32(None, None, 1, 1, 1, 3, None, None, None, None, 0, None)
     assert rc == -1 and b"null pointer" in lib.dicp_last_error()
     p = _lib.DicpParams()
-    rc = lib.dicp_icp_forward_f32(None, None, None, None, None, 1, 1, 1, 6, ctypes.byref(p), None, None, None, None, None, None, None,
+    rc = lib.dicp_icp_forward_f32(None, None, None, None, None, None, 1, 1, 1, 6, ctypes.byref(p), None, None, None, None, None, None, None,
                                   None, None, None, None, None, 0, None)
     assert rc == -1
 

@@ -746,6 +746,52 @@ def test_ragged_targets_use_valid_counts_not_pad_values():
 # ---------------------------------------------------------------------------------------
 # Gumbel-softmax soft NN (nn.py:43-70) as a streaming kernel
 # ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
+def test_ragged_sources_use_valid_counts_not_pad_rows(dtype, icp_type):
+    """SURVEY.md 8 f-1, source side: with n_valid the kernels never search or evaluate the padding rows of a ragged batch
+    (ICP.py:361-426 zero-pads and gives the pads weight 0).  (a) the list API equals the per-pair loop; (b) the same call
+    with NaN in the padding rows of the dense source and n_valid gives identical, finite results and gradients."""
+    from dicp_b200 import _functions
+    from oracle.dicp_oracle import make_wavy_pair
+    lens = [1300, 40, 2048, 517]
+    N, K = len(lens), 5
+    src, tgt = make_wavy_pair(N, max(lens), 1500, seed=99, dtype=dtype)
+    if icp_type == "pt2pt":
+        tgt = tgt[:, :, :3].contiguous()
+    tol = 1e-10 if dtype == torch.float64 else 2e-5
+    icp = _icp(icp_type, True, K, 1e-12, const_iter=True)
+    s_list = [src[b, :lens[b]].cuda() for b in range(N)]
+    t_list = [tgt[b].cuda() for b in range(N)]
+    T0 = torch.eye(4, dtype=dtype, device="cuda").repeat(N, 1, 1)
+    loss_fn = {"name": "cauchy", "metric": 0.5}
+    res = icp.icp(s_list, t_list, T0, trim_dist=2.0, loss_fn=loss_fn, dim=3)
+    R = 1 if icp_type == "pt2pl" else 3
+    for b in range(N):
+        one = icp.icp(s_list[b], t_list[b], T0[b], trim_dist=2.0, loss_fn=loss_fn, dim=3)
+        assert rel_err(res["T"][b].cpu(), one["T"][0].cpu()) < tol
+        assert rel_err(res["pc"][b, :lens[b]].cpu(), one["pc"][0].cpu()) < tol
+        assert rel_err(res["weights"][b, :, :lens[b] * R].cpu(), one["weights"][0].cpu()) < tol
+        assert float(res["weights"][b, :, lens[b] * R:].abs().max()) == 0.0 if lens[b] < max(lens) else True
+        assert torch.allclose(res["pc"][b, lens[b]:].cpu(), res["T"][b, :3, 3].cpu().expand(max(lens) - lens[b], 3))     # pads: C 0 + r
+    # (b) poisoned padding through the autograd node
+    dense = torch.stack([torch.cat((s_list[b], torch.full((max(lens) - lens[b], 3), float("nan"), dtype=dtype, device="cuda"))) for b in range(N)])
+    dense.requires_grad_(True)
+    t_d = torch.stack(t_list).requires_grad_(True)
+    p = _functions.make_params(icp_type, 3, True, "cauchy", 0.5, 2.0, 5.0, 1e-12, K, True, 0.0)
+    nv = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    w = torch.ones((N, max(lens)), dtype=dtype, device="cuda", requires_grad=True)
+    pc, T, deltas, weights = _functions.ICPFunction.apply(dense, t_d, T0, w, p, None, None, None, nv)[:4]
+    assert torch.isfinite(T).all() and torch.isfinite(weights).all() and torch.isfinite(deltas).all()
+    assert rel_err(T.detach().cpu(), res["T"].cpu()) < tol
+    wT = torch.arange(1, 13, dtype=dtype, device="cuda").reshape(3, 4)
+    (T[:, :3, :] * wT).sum().backward()
+    for b in range(N):
+        assert torch.isfinite(dense.grad[b, :lens[b]]).all() and torch.isfinite(w.grad[b, :lens[b]]).all()
+        assert float(dense.grad[b, lens[b]:].abs().sum()) == 0.0 and float(w.grad[b, lens[b]:].abs().sum()) == 0.0
+    assert torch.isfinite(t_d.grad).all()
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-4)])
 @pytest.mark.parametrize("S", [3, 6])
 def test_gumbel_nn_matches_formula_on_its_own_noise(dtype, tol, S):
