@@ -1,26 +1,30 @@
 #!/usr/bin/env python
-"""bench.py — ICP pairs/s (forward + backward, 10 constant iterations, 16k points).
+"""bench.py — ICP pairs/s (forward + backward, 10 constant iterations, 16k points), learning mode.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[2], SURVEY.md §8(d) "C3"): per GPU 256 cloud pairs x 16384
-source x 16384 target points, point-to-plane, Cauchy(0.5) + trim(2.0) weights, fp32, dim 3,
-T_init = I, const_iter, 10 iterations, forward + backward, synthetic wavy-surface clouds.
-One "step" = one pass of the hot path over one such batch.  Pairs are independent, so N GPUs
-process N x 256 pairs with no data-path collective (weak scaling; at N=8 this is configs[4]);
-in learning mode one NCCL all-reduce of [loss, d loss / d theta] closes every step.
+Workload (BASELINE.json configs[2] "C3" per GPU; configs[4] "C5" = 8 GPUs x this): per GPU 256 cloud pairs x 16384
+source x 16384 target points, point-to-plane, Cauchy(0.5) + trim(2.0) weights, fp32, dim 3, T_init = I, const_iter,
+10 iterations, forward + backward, synthetic wavy-surface clouds.  One "step" = one pass of the hot path over one such
+batch in LEARNING MODE: a per-point weight model (WeightModel: small MLP on the source coordinates + a
+64^3 voxel table, 0.26 M parameters) feeds `weight=`, the loss weighs the rows of T, the backward reaches the model
+(through grad_w, the 124-byte variant of the reverse point pass), the input clouds and T_init.  Pairs are independent,
+so N GPUs process N x 256 pairs with no data-path collective (weak scaling); one NCCL all-reduce of
+[loss | flattened parameter gradients] (1.05 MB) closes every step.
 
-`value`  : pairs/s with inputs resident in HBM (timed with CUDA events on the launch stream).
-`e2e`    : the same step (forward + backward) starting from pinned HOST buffers: the host->device
-           copies of the clouds and T_init, the call of the public API `dICP.ICP.ICP.icp`, the
-           backward to the input points and the device->host read of [loss, dloss/dtheta] and T
-           are all inside the timed region.
-`roofline`: the dominant kernel (nearest-neighbour scan, FP32 CUDA-core bound) timed alone
-           with CUDA events; `roofline_gn`: the Gauss-Newton accumulate (HBM bound).
-`cpu_baseline`: the oracle port of the reference's torch-CPU path on a bounded sample.
-`--impl reference`: the same oracle port timed alone on all host threads (the reference is
-           pure Python/torch and cannot travel to the GPU box).
+`value`      : pairs/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks).
+`e2e`        : the same step from pinned HOST buffers through the public API: every step's clouds and T_init are copied
+               host->device inside the timed region (double-buffered: the copy of step i+1 is enqueued on a side stream
+               before the kernels of step i, as an input pipeline would), and [loss, dloss/dtheta] and T are read back.
+`roofline`   : the dominant kernel (nearest-neighbour scan, FP32 CUDA-core bound); `frac` is the EXECUTED figure (3 FFMA
+               per evaluation, what ncu counts) against the nominal peak, next to the algorithmic 8-FLOP figure and a
+               measured FFMA issue peak (dicp_probe_fp32_flops).  `roofline_gn` / `roofline_bwd`: the two HBM-bound
+               per-correspondence kernels.
+`cpu_baseline` (N = 1 only) and `--impl reference`: the UNMODIFIED reference from baseline/_ref on the host cores, same
+               step (same weight model), a bounded sample of the workload.
+`theta_only` : round 1's step (weight=None, 13-float all-reduce) for continuity.
+`c4_split`   (N > 1): BASELINE configs[3] with the targets of the one pair split over the N GPUs.
 """
 import argparse
 import ctypes
@@ -110,6 +114,32 @@ def learning_loss(res, theta):
     return (res["T"][:, :3, :].reshape(-1, 12) * theta).sum()
 
 
+class WeightModel(torch.nn.Module):
+    """The learnable part of learning mode: a per-point prior weight for `weight=`,
+        w_i = sigmoid(MLP(p_i / extent) + table[voxel(p_i)] + 2),
+    a 3 -> 16 -> 1 MLP on the source coordinates plus a learnable 64^3 voxel table: 262 144 + 81 parameters, i.e.
+    1.05 MB of gradients in the all-reduce, at a per-point cost that stays small next to the ICP itself.  Plain torch
+    (it is the model being trained, not the hot path); identical in both arms (seeded init on the CPU)."""
+
+    def __init__(self, grid=64, hidden=16, extent=24.0):
+        super().__init__()
+        gen = torch.Generator().manual_seed(1234)
+        self.grid, self.extent = grid, extent
+        self.table = torch.nn.Parameter(0.1 * torch.randn(grid ** 3, generator=gen))
+        self.w1 = torch.nn.Parameter(torch.randn((3, hidden), generator=gen) / 3 ** 0.5)
+        self.b1 = torch.nn.Parameter(torch.zeros(hidden))
+        self.w2 = torch.nn.Parameter(torch.randn((hidden, 1), generator=gen) / hidden ** 0.5)
+        self.b2 = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, pts):
+        x = pts / self.extent
+        logit = (torch.tanh(x @ self.w1 + self.b1) @ self.w2 + self.b2).squeeze(-1)
+        cell = ((x * 0.5 + 0.5).clamp(0.0, 1.0 - 1e-6) * self.grid).long()
+        lin = (cell[..., 0] * self.grid + cell[..., 1]) * self.grid + cell[..., 2]
+        # index_select: its backward is an atomic index_add_ (the sort-based backward of advanced indexing costs 1 ms here)
+        return torch.sigmoid(logit + self.table.index_select(0, lin.reshape(-1)).reshape(lin.shape) + 2.0)
+
+
 # ---------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the UNMODIFIED reference from baseline/_ref (baseline/install_ref.py),
 # driven through its own public API and stock code path (dICP/ICP.py:46-303, dICP/nn.py:11-40).
@@ -118,6 +148,8 @@ def learning_loss(res, theta):
 def bench_config():
     """The `config` object of the JSON line; identical in both arms."""
     return {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "points": NPTS, "iterations": ITERS,
+            "learning_mode": "weight= from WeightModel (3-16-1 MLP + 64^3 voxel table, 262225 parameters); loss = sum(theta * T[:, :3, :]); "
+                             "backward to the model, the clouds and T_init; one all-reduce of [loss | flat gradients] per step",
             "l2": "inputs larger than L2 (source+target %.0f MB per GPU, plus 168 MB of saved correspondences "
                   "written and re-read per step)" % (PAIRS_PER_GPU * NPTS * 9 * 4 / 1e6)}
 
@@ -132,6 +164,7 @@ def cpu_arm():
     from baseline import ref_arm
     ref = ref_arm.load_reference()
     theta = torch.arange(1, 13, dtype=torch.float32)
+    model = WeightModel()
     if ref is not None:
         cfg_path = ref_arm.reference_config(const_iter=True)
         icp = ref.ICP(config_path=cfg_path, icp_type="pt2pl", max_iterations=ITERS, tolerance=1e-12, differentiable=True)
@@ -139,10 +172,11 @@ def cpu_arm():
         def step(src, tgt):
             s = src.clone().requires_grad_(True)
             t = tgt.clone().requires_grad_(True)
-            res = icp.icp(s, t, torch.eye(4).repeat(src.shape[0], 1, 1), trim_dist=TRIM, loss_fn=LOSS, dim=3)
+            model.zero_grad(set_to_none=True)
+            res = icp.icp(s, t, torch.eye(4).repeat(src.shape[0], 1, 1), weight=model(src), trim_dist=TRIM, loss_fn=LOSS, dim=3)
             learning_loss(res, theta).backward()
-            assert s.grad is not None and t.grad is not None and res["deltas"].shape[1] == ITERS
-            return float(res["T"].sum())
+            assert s.grad is not None and t.grad is not None and model.table.grad is not None and res["deltas"].shape[1] == ITERS
+            return float(res["T"].detach().sum())
         kind = "reference"
     else:
         from oracle.dicp_oracle import IcpSettings, icp_forward
@@ -152,9 +186,10 @@ def cpu_arm():
         def step(src, tgt):
             s = src.clone().requires_grad_(True)
             t = tgt.clone().requires_grad_(True)
-            res = icp_forward(s, t, torch.eye(4).repeat(src.shape[0], 1, 1), torch.ones(src.shape[:2]), cfg)
+            model.zero_grad(set_to_none=True)
+            res = icp_forward(s, t, torch.eye(4).repeat(src.shape[0], 1, 1), model(src), cfg)
             learning_loss(res, theta).backward()
-            return float(res["T"].sum())
+            return float(res["T"].detach().sum())
         kind = "port"
     _CPU_ARM.update(kind=kind, step=step)
     return kind, step
@@ -217,6 +252,21 @@ def time_kernel(fn, reps, warm=3):
     return best
 
 
+def measured_fp32_peak(dev):
+    """TFLOP/s a loop of independent FFMAs reaches on this device (dicp_probe_fp32_flops, CUDA events)."""
+    from dicp_b200 import _lib
+    lib = _lib.load_library()
+    sink = torch.zeros(1, device=dev)
+    st = _lib.stream_ptr(dev)
+    flop = [0.0]
+
+    def launch():
+        flop[0] = lib.dicp_probe_fp32_flops(4096, _lib.ptr(sink), st)
+
+    sec = time_kernel(launch, reps=5)
+    return flop[0] / sec / 1e12 if flop[0] > 0 else None
+
+
 def roofline_nn(src, tgt, pk):
     """NN scan kernel alone (dicp_nn_scan_f32), CUDA events on the launch stream."""
     from dicp_b200 import _lib
@@ -234,20 +284,24 @@ def roofline_nn(src, tgt, pk):
 
     sec = time_kernel(launch, reps=5)
     evals = float(N) * n * m
-    flop = 8.0 * evals                       # algorithmic: 3 sub, 3 mul, 2 add per (query, target) evaluation
-    peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-    ach = flop / sec / 1e12
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    algorithmic = 8.0 * evals / sec / 1e12   # 3 sub, 3 mul, 2 add per (query, target) evaluation
     executed = 6.0 * evals / sec / 1e12      # what the filter scan issues: 3 FFMA per evaluation (refine + fallback < 2 % more)
+    probe = measured_fp32_peak(dev)
     return {"kernel": "nn_scan_f32_kernel<8> + exact fallback (one dicp_nn_scan_f32 call)", "bound": "fp32",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of nn_scan_f32_kernel<8> at these shapes (profiles/r01_ncu_full_top_kernels.md)
-            "traffic": 201.7e6 if (N, n, m) == (256, 16384, 16384) else None, "ms_per_launch": sec * 1e3,
-            "executed_tflops": executed, "frac_executed": executed / peak,
-            "peak_source": "148 SMs x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json has no FP32 CUDA-core figure)" % pk["source"],
-            # context: a loop of independent FFMAs issues at 1.13 cycles per warp instruction and scheduler on this part
-            # (tools/ubench_fp32.cu, profiles/r01_nn_tuning.md), i.e. 88 % of the nominal peak is the most FFMA code reaches
-            "ffma_issue_peak_measured": peak / 1.13, "frac_executed_of_ffma_issue_peak": executed / (peak / 1.13),
+            "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
+            "achieved_algorithmic": algorithmic, "frac_algorithmic": algorithmic / peak,
+            "peak_measured_ffma": probe, "frac_of_measured_ffma_peak": executed / probe if probe else None,
+            "traffic": NCU_TRAFFIC.get(("nn", N, n, m)), "ms_per_launch": sec * 1e3,
+            "peak_source": "nominal: %d SMs x 128 lanes x 2 x sm_max_mhz (%s; MEASURED_PEAKS.json has no FP32 CUDA-core figure); "
+                           "peak_measured_ffma: independent FFMA chains timed in this run" % (sms, pk["source"]),
             "flop_per_pair_eval": {"algorithmic": 8, "executed": 6}, "units_per_launch": evals}, idx
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of this round's kernels at the C3
+# shape (profiles/r02_ncu_top_kernels.md); other shapes have no capture -> null
+NCU_TRAFFIC = {("nn", 256, 16384, 16384): 201.7e6, ("gn", 256, 16384, 16384): 229.6e6, ("bwd", 256, 16384, 16384): 523.8e6}
 
 
 def roofline_gn(src, tgt, idx, pk):
@@ -273,10 +327,9 @@ def roofline_gn(src, tgt, idx, pk):
     sec = time_kernel(launch, reps=20)
     nbytes = 48.0 * N * n                    # p 12 + gathered (q,n) 24 + idx 4 + w_init 4 + weights write 4
     ach = nbytes / sec / 1e9
-    return {"kernel": "gn_accum_kernel<float,pt2pl,3> (one dicp_gn_accumulate_f32 call = the loop's single launch)", "bound": "hbm",
+    return {"kernel": "gn_accum_staged_kernel<pt2pl,3> (one dicp_gn_accumulate_f32 call = the loop's single launch)", "bound": "hbm",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            # dram bytes of gn_accum_kernel at 256 pairs from the ncu capture in profiles/: 201.5 MB read + 15.8 MB written
-            "traffic": 217.3e6 if (N, n, m) == (256, 16384, 16384) else None,
+            "traffic": NCU_TRAFFIC.get(("gn", N, n, m)),
             "ms_per_launch": sec * 1e3, "peak_source": pk["source"], "bytes_per_correspondence": 48,
             "units_per_launch": float(N) * n, "pairs": N}
 
@@ -316,14 +369,15 @@ def roofline_bwd(src, tgt, pk, with_weight):
     nbytes = per * N * n
     ach = nbytes / sec / 1e9
     return {"kernel": "bwd_points_staged_kernel<pt2pl> + bwd_pair_kernel, one reverse iteration", "bound": "hbm", "achieved": ach,
-            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "ms_per_launch": sec * 1e3,
-            "bytes_per_correspondence": per, "with_weight_gradient": with_weight, "units_per_launch": float(N) * n, "pairs": N,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(("bwd", N, n, m)),
+            "ms_per_launch": sec * 1e3, "bytes_per_correspondence": per, "with_weight_gradient": with_weight, "units_per_launch": float(N) * n, "pairs": N,
             "whole_backward_ms": t10 * 1e3, "peak_source": pk["source"]}
 
 
 def run_ours(args):
     import torch.distributed as dist
     from dicp_b200.ICP import ICP          # `dICP.ICP.ICP` of the drop-in alias package is this class
+    from dicp_b200 import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -341,41 +395,79 @@ def run_ours(args):
     icp.const_iter = True
     icp.device = dev
     theta = torch.arange(1, 13, dtype=torch.float32, device=dev).requires_grad_(True)
+    model = WeightModel().to(dev)
+    params = list(model.parameters()) + [theta]
+    n_params = sum(p.numel() for p in params)
 
     src_d = src_h.to(dev).requires_grad_(True)
     tgt_d = tgt_h.to(dev).requires_grad_(True)
     T0_d = T0_h.to(dev)
 
-    def allreduce(vec):
-        if world > 1:
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-        return vec
+    def learning_step(s, t, T0):
+        """weight model -> ICP forward -> loss -> backward (model, clouds, T_init) -> one all-reduce of [loss | flat grads]"""
+        for p_ in params:
+            p_.grad = None
+        res = icp.icp(s, t, T0, weight=model(s.detach()), trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        loss = learning_loss(res, theta)
+        loss.backward()
+        return parallel.allreduce_loss_and_grads(loss, params), res
 
     def step_resident():
-        """inputs already in HBM; forward + backward; learning-mode all-reduce of [loss, dloss/dtheta]."""
+        src_d.grad = tgt_d.grad = None
+        return learning_step(src_d, tgt_d, T0_d)[0]
+
+    def step_theta_only():
+        """round 1's step: weight=None, all-reduce of [loss, dloss/dtheta] (13 floats)"""
         src_d.grad = tgt_d.grad = theta.grad = None
         res = icp.icp(src_d, tgt_d, T0_d, trim_dist=TRIM, loss_fn=LOSS, dim=3)
         loss = learning_loss(res, theta)
         loss.backward()
-        return allreduce(torch.cat((loss.detach().reshape(1), theta.grad)))
+        vec = torch.cat((loss.detach().reshape(1), theta.grad))
+        if world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        return vec
 
-    def step_e2e():
-        """the same step from pinned HOST buffers: the clouds and T_init are copied to the GPU inside the step (H2D),
-        `icp.icp` runs forward, the backward reaches the input points as in step_resident, and the reduced
-        [loss, dloss/dtheta] and the transforms are read back to the host (D2H)."""
-        theta.grad = None
-        s = src_h.to(dev, non_blocking=True).requires_grad_(True)
-        t = tgt_h.to(dev, non_blocking=True).requires_grad_(True)
-        res = icp.icp(s, t, T0_h.to(dev, non_blocking=True), trim_dist=TRIM, loss_fn=LOSS, dim=3)
-        loss = learning_loss(res, theta)
-        loss.backward()
-        assert s.grad is not None and t.grad is not None
-        out = allreduce(torch.cat((loss.detach().reshape(1), theta.grad)))
-        return out.cpu(), res["T"].detach().cpu()
+    # e2e: pinned host buffers -> device, double-buffered on a side stream (the copy of step i+1 is enqueued before the
+    # kernels of step i), public API, read-back of the reduced loss and of T
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{"src": torch.empty_like(src_d.detach()), "tgt": torch.empty_like(tgt_d.detach()), "T0": torch.empty_like(T0_d),
+              "ready": torch.cuda.Event(), "free": torch.cuda.Event()} for _ in range(2)]
 
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
+    def enqueue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot["free"])          # the step that last used this slot has finished
+            slot["src"].copy_(src_h, non_blocking=True)
+            slot["tgt"].copy_(tgt_h, non_blocking=True)
+            slot["T0"].copy_(T0_h, non_blocking=True)
+            slot["ready"].record(copy_stream)
+
+    def e2e_loop(steps):
+        cur = torch.cuda.current_stream(dev)
+        for sl in slots:
+            sl["free"].record(cur)
+        enqueue_copy(slots[0])
+        out = None
+        for i in range(steps):
+            sl = slots[i % 2]
+            if i + 1 < steps:
+                enqueue_copy(slots[(i + 1) % 2])
+            cur.wait_event(sl["ready"])
+            s = sl["src"].requires_grad_(True)
+            t = sl["tgt"].requires_grad_(True)
+            loss, res = learning_step(s, t, sl["T0"])
+            assert s.grad is not None and t.grad is not None
+            out = (torch.cat((loss.reshape(1), theta.grad)).cpu(), res["T"].detach().cpu())       # D2H: the step's result
+            sl["src"].requires_grad_(False)
+            sl["tgt"].requires_grad_(False)
+            sl["free"].record(cur)
+        return out
+
+    def timed(fn, steps, warmup, sampler=None, loop=False):
+        if loop:
+            fn(max(1, warmup))
+        else:
+            for _ in range(warmup):
+                fn()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -383,8 +475,11 @@ def run_ours(args):
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        if loop:
+            fn(steps)
+        else:
+            for _ in range(steps):
+                fn()
         e1.record()
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
@@ -397,25 +492,54 @@ def run_ours(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     sec, clocks = timed(step_resident, args.steps, args.warmup, sampler)
-    sec_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
-    steps_e2e = max(2, args.steps // 2)
+    steps_e2e = max(3, args.steps // 2)
+    sec_e2e, _ = timed(e2e_loop, steps_e2e, 1, loop=True)
+    steps_aux = max(3, args.steps // 2)
+    sec_theta, _ = timed(step_theta_only, steps_aux, 1)
     pairs_total = PAIRS_PER_GPU * world
-    # the same workload with the exact uniform-grid search (SURVEY.md §8 f-3; identical correspondences)
+    # the same workload with the exact uniform-grid search (SURVEY.md 8 f-3; identical correspondences)
     icp.nn_search = "grid"
-    sec_grid, _ = timed(step_resident, args.steps, args.warmup)
-    sec_grid_e2e, _ = timed(step_e2e, steps_e2e, 1)
+    sec_grid, _ = timed(step_resident, steps_aux, 1)
+    sec_grid_e2e, _ = timed(e2e_loop, steps_aux, 1, loop=True)
     icp.nn_search = "brute"
 
-    line = None
+    # the collective alone: [loss | flat gradients] SUM all-reduce, as the step issues it
+    coll = {"elements": 1 + n_params, "bytes": 4 * (1 + n_params), "ms": 0.0, "backend": "nccl" if world > 1 else "none (single GPU)"}
+    if world > 1:
+        buf = torch.zeros(1 + n_params, device=dev)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(buf)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        coll["ms"] = float(ms.item())
+
+    # BASELINE configs[3] with the targets of the one pair split over the N GPUs
+    c4 = c4_split_record(icp, dev, rank, world) if world > 1 else None
+
     if rank == 0:
         roof, idx = roofline_nn(src_d.detach(), tgt_d.detach(), pk)
         roof_gn = roofline_gn(src_d.detach(), tgt_d.detach(), idx, pk)
-        # the same kernel at C5-on-one-GPU size, 2048 pairs = 33.5 M correspondences (measure the
-        # HBM fraction where launch latency does not dominate)
+        # the same kernels at C5-on-one-GPU size, 2048 pairs = 33.5 M correspondences (measure the
+        # HBM fraction where launch ramp and tail do not dominate)
         big = 8
-        roof_gn["at_%d_pairs" % (big * PAIRS_PER_GPU)] = {
-            k: v for k, v in roofline_gn(src_d.detach().repeat(big, 1, 1), tgt_d.detach().repeat(big, 1, 1), idx.repeat(big, 1), pk).items()
-            if k in ("achieved", "frac", "ms_per_launch", "units_per_launch")}
+        big_src, big_tgt = src_d.detach().repeat(big, 1, 1), tgt_d.detach().repeat(big, 1, 1)
+        keep = ("achieved", "frac", "ms_per_launch", "units_per_launch")
+        roof_gn["at_%d_pairs" % (big * PAIRS_PER_GPU)] = {k: v for k, v in roofline_gn(big_src, big_tgt, idx.repeat(big, 1), pk).items() if k in keep}
+        del big_src, big_tgt
+        roof_bwd = roofline_bwd(src_d.detach(), tgt_d.detach(), pk, True)
+        roof_bwd["without_weight_gradient"] = {k: v for k, v in roofline_bwd(src_d.detach(), tgt_d.detach(), pk, False).items()
+                                               if k in keep + ("bytes_per_correspondence",)}
+        mid = 4
+        roof_bwd["at_%d_pairs" % (mid * PAIRS_PER_GPU)] = {
+            k: v for k, v in roofline_bwd(src_d.detach().repeat(mid, 1, 1), tgt_d.detach().repeat(mid, 1, 1), pk, True).items() if k in keep}
         cpu = None
         if world == 1:    # rank 0 at N=1 only: a bounded sample (8 x 1 pair, 10-30 s of CPU work); at N>1 the ranks waiting
             # in the barrier would starve it, and the driver's own reference arm covers those N
@@ -430,14 +554,12 @@ def run_ours(args):
                 cpu_step(s1, t1)
             cdt = time.perf_counter() - t0
             cpu = {"value": reps / cdt, "unit": "pairs/s", "cores": cores, "kind": kind,
-                   "sample": "%d x 1 pair of the C3 workload (fwd+bwd, 10 it), %s, %d threads, %.1f s"
+                   "sample": "%d x 1 pair of the C3 workload (fwd+bwd, 10 it, learning mode), %s, %d threads, %.1f s"
                              % (reps, CPU_ARM_DESCRIPTION[kind], torch.get_num_threads(), cdt)}
-        # kernels of libdicp_b200.so per step (profiles/r01_launches.md): forward init, bbox centres, NN pack, gather
-        # records + 10 x (filter scan, exact fallback, unpack, GN accumulate, GN update) + finalize;
-        # backward seed + 10 x (pair, points) + final pair
-        launches_per_step = (4 + 5 * ITERS + 1) + (1 + 2 * ITERS + 1)
-        # per step: clouds + T_init up; T and the reduced [loss, dloss/dtheta] down (pc / weights / deltas / costs and
-        # the gradients of the clouds stay on the GPU, where a training loop would consume them)
+        # kernels of libdicp_b200.so per step: forward init, bbox centres, NN pack, gather records + 10 x (filter scan, exact
+        # fallback, unpack, GN accumulate, GN update) + finalize; backward gather records, seed + 10 x (pair, points) +
+        # final pair + gradient-table fold (memsets and the torch ops of the weight model are not counted)
+        launches_per_step = (4 + 5 * ITERS + 1) + (2 + 2 * ITERS + 2)
         h2d = (src_h.numel() + tgt_h.numel() + T0_h.numel()) * 4
         d2h = (PAIRS_PER_GPU * 16 + 13) * 4
         line = {
@@ -445,22 +567,85 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(), "pairs_total": pairs_total,
-            "learning_mode_allreduce": "13 floats per step over NCCL" if world > 1 else "single GPU: no collective",
+            "learning_mode_allreduce": coll,
             "clocks": clocks,
             "e2e": {"value": pairs_total * steps_e2e / sec_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * sec_e2e / steps_e2e, "api": "pinned host clouds -> H2D -> dICP.ICP.ICP.icp (forward) -> backward to the input points -> D2H of [loss, dloss/dtheta] and T"},
+                    "ms_per_step": 1e3 * sec_e2e / steps_e2e,
+                    "api": "pinned host clouds -> H2D (double-buffered on a side stream) -> WeightModel -> dICP.ICP.ICP.icp -> backward to the "
+                           "model, the input points and T_init -> all-reduce -> D2H of [loss, dloss/dtheta] and T",
+                    "note": "the gradients of the clouds (151 MB) and of the weight model stay on the GPU, where the optimiser of a training "
+                            "loop consumes them; a caller who passes HOST tensors to icp() gets pc / weights copied back lazily (dicp_b200.ICP._Results)"},
             "gpu_launches": launches_per_step * args.steps,
             "nn_search": "brute (tiled brute-force scan, the north-star kernel)",
-            "alt_nn_grid": {"value": pairs_total * args.steps / sec_grid, "unit": "pairs/s", "ms_per_step": 1e3 * sec_grid / args.steps,
-                            "e2e": pairs_total * steps_e2e / sec_grid_e2e,
+            "theta_only": {"value": pairs_total * steps_aux / sec_theta, "unit": "pairs/s", "ms_per_step": 1e3 * sec_theta / steps_aux,
+                           "note": "round 1's step: weight=None, all-reduce of 13 floats"},
+            "alt_nn_grid": {"value": pairs_total * steps_aux / sec_grid, "unit": "pairs/s", "ms_per_step": 1e3 * sec_grid / steps_aux,
+                            "e2e": pairs_total * steps_aux / sec_grid_e2e,
                             "note": "same workload with ICP.nn_search='grid': exact uniform-grid NN built once per call, "
                                     "bit-identical correspondences (tests/test_gpu_parity.py::test_icp_grid_mode_equals_brute_mode)"},
-            "roofline": roof, "roofline_gn": roof_gn, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_gn": roof_gn, "roofline_bwd": roof_bwd, "cpu_baseline": cpu, "c4_split": c4,
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def c4_split_record(icp_unused, dev, rank, world):
+    """BASELINE configs[3] (one 130 000 x 130 000 pair, pt2pl, fwd+bwd, 10 it) with the TARGETS split over the ranks
+    (parallel.SplitTargetSearch: slice scans + one MIN merge per iteration over NVLink peer memory or NCCL); rank 0 also runs
+    the plain single-GPU call and checks the split run reproduces it bit for bit.  Timing: CUDA events, max over ranks."""
+    import torch.distributed as dist
+    from dicp_b200.ICP import ICP
+    from dicp_b200.parallel import SplitTargetSearch
+    from dicp_b200.synthetic import surface_pairs
+    src, tgt = surface_pairs(1, 130000, 130000, seed=4000, dtype=torch.float32, extent=60.0)
+    src, tgt = src.to(dev), tgt.to(dev)
+    T0 = torch.eye(4, device=dev)[None]
+    theta = torch.arange(1, 13, dtype=torch.float32, device=dev)
+
+    def step(search):
+        icp = ICP(icp_type="pt2pl", differentiable=True, max_iterations=ITERS, tolerance=1e-12)
+        icp.const_iter = True
+        icp.nn_search = search
+        s, t = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+        res = icp.icp(s, t, T0, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        (res["T"][:, :3, :].reshape(-1, 12) * theta).sum().backward()
+        return res["T"].detach(), s.grad
+
+    def timed(search, reps, warm):
+        for _ in range(warm):
+            out = step(search)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            out = step(search)
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    search = SplitTargetSearch(transport="auto")
+    ms_split, (T_split, g_split) = timed(search, 4, 2)
+    rec = {"workload": "C4: 1 pair x 130000 x 130000, pt2pl, cauchy(0.5)+trim(2.0), fp32, 10 it, fwd+bwd, targets split over %d GPUs" % world,
+           "ms_per_step": ms_split, "pairs_per_s": 1e3 / ms_split, "transport": search.used_transport}
+    if rank == 0:
+        step("brute")
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            T_one, g_one = step("brute")
+        b.record()
+        torch.cuda.synchronize()
+        rec["single_gpu_ms_per_step"] = a.elapsed_time(b) / 3
+        rec["speedup"] = rec["single_gpu_ms_per_step"] / ms_split
+        rec["bit_identical_to_single_gpu"] = bool(torch.equal(T_one, T_split) and torch.equal(g_one, g_split))
+    dist.barrier()
+    return rec
 
 
 def main():

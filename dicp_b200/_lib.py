@@ -75,6 +75,7 @@ _SIGNATURES["dicp_nn_unpack_keys_f32"] = ([_P, _Z, _P, _P, _P], _I)
 for _s in ("f32", "f64"):
     _SIGNATURES["dicp_solve_update_" + _s] = ([_P, _I, _P, _I, ctypes.POINTER(DicpParams), _P, _P, _P, _P], _I)
 _SIGNATURES["dicp_gn_blocks_per_pair"] = ([_I, _I], _I)
+_SIGNATURES["dicp_probe_fp32_flops"] = ([_I, _P, _P], ctypes.c_double)
 _SIGNATURES["dicp_gn_rows_bytes"] = ([_I, _I, _I], _Z)
 _SIGNATURES["dicp_gn_pack_rows_f32"] = ([_P, _I, _I, _I, _I, _P, _P], _I)
 

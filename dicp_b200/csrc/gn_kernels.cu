@@ -460,7 +460,8 @@ template <typename T>
 int gn_pack_rows(const T* target, int N, int m, int S, bool pt2pl, void* rows, cudaStream_t st) {
   if constexpr (sizeof(T) == 4) {
     const size_t total = (size_t)N * m;
-    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    const size_t cap = (size_t)device_sm_count() * 32;
+    const int grid = (int)((total + 255) / 256 < cap ? (total + 255) / 256 : cap);
     if (pt2pl) gn_pack_rows_kernel<true><<<grid, 256, 0, st>>>(target, total, S, (float4*)rows);
     else gn_pack_rows_kernel<false><<<grid, 256, 0, st>>>(target, total, S, (float4*)rows);
     DICP_LAUNCH_CHECK();

@@ -29,6 +29,7 @@
 // The target range is split over blockIdx.z when that is needed to fill 148 SMs or to keep the
 // tail wave short; partial (d2, idx) results are merged in split order (earlier split wins ties).
 #include "common.cuh"
+#include "tile_stream.cuh"
 
 namespace dicp {
 
@@ -746,7 +747,7 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
   p.gx = (n + p.threads * p.q - 1) / (p.threads * p.q);
   const int tiles_total = (m_pad + p.tile - 1) / p.tile;
   const long long base = (long long)p.gx * N;
-  const long long slots = 148LL * ctas_per_sm;
+  const long long slots = (long long)device_sm_count() * ctas_per_sm;
   const long long want = slots * 6;          // >= 6 waves => the short last wave costs a few percent at most
   long long s = (want + base - 1) / base;
   const long long max_by_work = tiles_total / 8 > 0 ? tiles_total / 8 : 1;   // >= 8 tiles per CTA keeps prologue/refine overhead small
@@ -822,7 +823,7 @@ static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const f
   // CTAs stride over the lists (their lengths are only known on the device).  Few CTAs per pair when
   // there are many pairs (empty CTAs are not free), enough to fill the machine when there are few.
   const int gx_cap = (w.fb_cap + FBF_THREADS * FBF_Q - 1) / (FBF_THREADS * FBF_Q);
-  int gx = (148 * 8 + N * fs - 1) / (N * fs);
+  int gx = (device_sm_count() * 8 + N * fs - 1) / (N * fs);
   if (gx < 4) gx = 4;
   if (gx > gx_cap) gx = gx_cap;
   dim3 grid(gx, N, fs);
@@ -937,9 +938,32 @@ nn_unpack_keys_kernel(const unsigned long long* __restrict__ keys, size_t count,
   }
 }
 
+// FP32 CUDA-core issue-rate probe: what a loop of independent FFMAs reaches on this device (the denominator of the
+// scan's roofline; MEASURED_PEAKS.json has no FP32 figure).  16 independent accumulator chains per thread, 8 warps per
+// CTA, 8 CTAs per SM; operands live in registers only.  bench.py times it with CUDA events.
+__global__ void __launch_bounds__(256)
+probe_ffma_kernel(int iters, float seed, float* __restrict__ sink) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i);
+  const float m = 1.0f + seed * 1e-9f, c = seed * 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = __fmaf_rn(a[i], m, c);
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) sink[0] = s;               // keeps the chains alive, practically never true
+}
+
 static int grid_for(size_t count) {
   const size_t b = (count + 255) / 256;
-  return (int)(b < 148 * 8 ? (b > 0 ? b : 1) : 148 * 8);
+  const size_t cap = (size_t)device_sm_count() * 8;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
 }  // namespace dicp
@@ -989,6 +1013,13 @@ int dicp_nn_unpack_keys_f32(const void* keys, size_t count, int32_t* idx_out, fl
   dicp::nn_unpack_keys_kernel<<<dicp::grid_for(count), 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)keys, count, idx_out, d2_out);
   DICP_LAUNCH_CHECK();
   return 0;
+}
+double dicp_probe_fp32_flops(int iters, float* sink, void* stream) {
+  if (iters < 1 || sink == nullptr) return 0.0;
+  const int grid = dicp::device_sm_count() * 8;
+  dicp::probe_ffma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, sink);
+  if (cudaGetLastError() != cudaSuccess) return 0.0;
+  return 2.0 * 16.0 * 8.0 * (double)iters * 256.0 * (double)grid;      // FLOP of the launch
 }
 int dicp_gather_rows_f32(const float* tgt, const int32_t* idx, int N, int n, int m, int S, float* out, void* stream) {
   return dicp::gather_impl<float>(tgt, idx, N, n, m, S, out, stream, false);

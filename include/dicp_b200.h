@@ -132,6 +132,11 @@ DICP_API int dicp_nn_push_keys_f32(const float* d2, const int32_t* idx, int offs
                           const uint64_t* peer_bufs, int world, int first_peer, void* reset_buf, void* stream);
 DICP_API int dicp_nn_unpack_keys_f32(const void* keys, size_t count, int32_t* idx_out, float* d2_out, void* stream);
 
+/* FP32 CUDA-core probe for the roofline of the scan: launches a kernel of independent FFMA chains (8 CTAs of 256
+ * threads per SM, 16 chains per thread, 8 x 16 FFMAs per loop iteration) and returns the FLOP count of the launch
+ * (0 on error); the caller times it on `stream`.  sink: any device float.                                      */
+DICP_API double dicp_probe_fp32_flops(int iters, float* sink, void* stream);
+
 /* ---- neighbour gather and its adjoint: replaces repeat+gather at dICP/nn.py:37-38 ------
  * out[b,i,:] = tgt[b,idx[b,i],:]           grad_tgt[b,idx[b,i],:] += grad_out[b,i,:]
  * grad_tgt must be zero-initialised by the caller (it is accumulated into).             */
