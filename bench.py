@@ -492,7 +492,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     sec, clocks = timed(step_resident, args.steps, args.warmup, sampler)
-    steps_e2e = max(3, args.steps // 2)
+    steps_e2e = max(3, args.steps)       # as many steps as the resident run: the unoverlapped first copy of the pipeline is amortised alike
     sec_e2e, _ = timed(e2e_loop, steps_e2e, 1, loop=True)
     steps_aux = max(3, args.steps // 2)
     sec_theta, _ = timed(step_theta_only, steps_aux, 1)

@@ -154,9 +154,7 @@ template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 constexpr int NN_CHUNK = 32;
 inline int nn_m_pad(int m) { return (m + NN_CHUNK - 1) / NN_CHUNK * NN_CHUNK; }
-inline size_t nn_packed_bytes(int N, int m, int elem_size) {
-  return elem_size == 4 ? align_up(((size_t)N * nn_m_pad(m) * 2 + (size_t)N) * 16) : align_up((size_t)N * nn_m_pad(m) * 32);
-}
+size_t nn_packed_bytes(int N, int m, int elem_size);     // nn_kernels.cu (depends on the fp32 record layout chosen there)
 
 template <typename T>
 int nn_pack_targets(const T* tgt, int N, int m, int S, const int32_t* m_valid, typename Vec4<T>::type* packed, cudaStream_t st);

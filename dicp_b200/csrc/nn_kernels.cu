@@ -86,6 +86,25 @@ __global__ void nn_center_kernel(const T* __restrict__ tgt, int m_all, int S, co
   }
 }
 
+// NNF_PACKED = 1 (experiment, off): the filter on packed fma.rn.f32x2 (FFMA2), two queries per instruction, explicit
+// 64-bit register pairs for the query components and the running sums.  The idea: a 64-bit operand reads both
+// register banks at once, so the scalar loop's same-parity collisions between the query component and the running
+// sum (29 % of its FFMAs) cannot happen, and the FFMAs need half the issue slots.  The filter records are then stored
+// with every component duplicated, (ax,ax,ay,ay | az,az,aw,aw) = 32 bytes, so that a record arrives as four
+// ready-made 64-bit operands with two LDS.128.  Measured at C3 (round 2): 10.4 ms per scan against 8.64 ms scalar --
+// three 64-bit operands per FFMA2 are more register bandwidth than the file delivers in two cycles -- so the scalar
+// loop stays; results are bit-identical either way (same IEEE FMAs).
+#ifndef NNF_PACKED
+#define NNF_PACKED 0
+#endif
+constexpr int NNF_FREC = NNF_PACKED ? 2 : 1;        // float4 units per filter record
+// views into the fp32 packed buffer: [N, m_pad] filter records | [N, m_pad] original (x,y,z,0) | [N] centres
+__host__ __device__ inline const float4* nn_orig_records(const float4* packed, int N, int m_pad) { return packed + (size_t)NNF_FREC * N * m_pad; }
+__host__ __device__ inline const float4* nn_centers(const float4* packed, int N, int m_pad) { return packed + (size_t)(NNF_FREC + 1) * N * m_pad; }
+size_t nn_packed_bytes(int N, int m, int elem_size) {
+  return elem_size == 4 ? align_up(((size_t)N * nn_m_pad(m) * (NNF_FREC + 1) + (size_t)N) * 16) : align_up((size_t)N * nn_m_pad(m) * 32);
+}
+
 __global__ void nn_pack_f32_kernel(const float* __restrict__ tgt, int m, int m_pad, int S, const int32_t* __restrict__ m_valid,
                                    const float4* __restrict__ centers, float4* __restrict__ filt, float4* __restrict__ orig) {
   const int b = blockIdx.y;
@@ -105,7 +124,12 @@ __global__ void nn_pack_f32_kernel(const float* __restrict__ tgt, int m, int m_p
     f = make_float4(-2.0f * far, -2.0f * far, -2.0f * far, 3.0f * far * far);
     o = make_float4(far, far, far, 0.0f);
   }
-  filt[(size_t)b * m_pad + j] = f;
+  if (NNF_PACKED) {
+    filt[((size_t)b * m_pad + j) * 2] = make_float4(f.x, f.x, f.y, f.y);
+    filt[((size_t)b * m_pad + j) * 2 + 1] = make_float4(f.z, f.z, f.w, f.w);
+  } else {
+    filt[(size_t)b * m_pad + j] = f;
+  }
   orig[(size_t)b * m_pad + j] = o;
 }
 
@@ -125,15 +149,11 @@ __global__ void nn_pack_f64_kernel(const double* __restrict__ tgt, int m, int m_
   packed[(size_t)b * m_pad + j] = v;
 }
 
-// views into the fp32 packed buffer
-__host__ __device__ inline const float4* nn_orig_records(const float4* packed, int N, int m_pad) { return packed + (size_t)N * m_pad; }
-__host__ __device__ inline const float4* nn_centers(const float4* packed, int N, int m_pad) { return packed + 2 * (size_t)N * m_pad; }
-
 template <>
 int nn_pack_targets<float>(const float* tgt, int N, int m, int S, const int32_t* m_valid, float4* packed, cudaStream_t st) {
   const int m_pad = nn_m_pad(m);
-  float4* orig = packed + (size_t)N * m_pad;
-  float4* centers = packed + 2 * (size_t)N * m_pad;
+  float4* orig = packed + (size_t)NNF_FREC * N * m_pad;
+  float4* centers = packed + (size_t)(NNF_FREC + 1) * N * m_pad;
   nn_center_kernel<float><<<N, 256, 0, st>>>(tgt, m, S, m_valid, centers);
   DICP_LAUNCH_CHECK();
   dim3 grid((m_pad + 255) / 256, N);
@@ -310,6 +330,9 @@ constexpr int NNF_THREADS = 128;
 #ifndef NNF_IL
 #define NNF_IL 8
 #endif
+#ifndef NNF_PIL
+#define NNF_PIL 4          // records interleaved per thread in the packed loop
+#endif
 #ifndef NNF_ORDER
 #define NNF_ORDER 1
 #endif
@@ -317,7 +340,21 @@ constexpr int NNF_THREADS = 128;
 #define NNF_XQUAD 1
 #endif
 #define NNF_FMA(xv, av, cv) __fmaf_rn(xv, av, cv)
-constexpr int NNF_TILE = NNF_TILE_RECORDS;     // records per shared-memory stage (16 KB; two stages, 5 CTAs per SM)
+constexpr int NNF_TILE = NNF_TILE_RECORDS / NNF_FREC;     // records per shared-memory stage (16 KB; two stages, 5 CTAs per SM)
+#if NNF_PACKED
+typedef unsigned long long nnf_u64;
+__device__ __forceinline__ nnf_u64 ffma2(nnf_u64 a, nnf_u64 b, nnf_u64 c) {
+  nnf_u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ nnf_u64 pack2(float lo, float hi) {
+  nnf_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(nnf_u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+#endif
 
 // Filter margin of one query, in the translated frame (x = x', y = y' below).  u = 2^-24.
 // The filter value of target y is
@@ -351,7 +388,7 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
                    int32_t* __restrict__ fb_list, float* __restrict__ fb_thr, int fb_cap, unsigned long long* __restrict__ fb_key,
                    const int* __restrict__ stop_flag, const int32_t* __restrict__ n_valid) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
-  __shared__ __align__(16) float4 tile[2][NNF_TILE];
+  __shared__ __align__(16) float4 tile[2][NNF_TILE * NNF_FREC];
   const float INF = Sentinel<float>::inf();
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -370,7 +407,7 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
     }
     return;
   }
-  const float4* tg = packed + (size_t)b * m_pad;
+  const float4* tg = packed + (size_t)b * m_pad * NNF_FREC;
   const float4* tg_orig = nn_orig_records(packed, N, m_pad) + (size_t)b * m_pad;
   const float4 ctr = nn_centers(packed, N, m_pad)[b];
 
@@ -405,7 +442,7 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
 #if NNF_XQUAD
   // Round trip of (x', best) through shared memory with a 128-bit load: the load's destination is an aligned
   // register quad, which pins x'_0, x'_1, x'_2 of every query to register banks 0, 1, 2 for the whole scan.
-  static_assert(NNF_TILE >= NNF_THREADS * Q, "the second tile buffer stages the queries");
+  static_assert(NNF_TILE * NNF_FREC >= NNF_THREADS * Q, "the second tile buffer stages the queries");
 #pragma unroll
 #ifndef NNF_XROT
 #define NNF_XROT 3
@@ -433,10 +470,18 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
 
   auto issue_tile = [&](int t, int buf) {
     const int start = t * NNF_TILE;
-    const int cnt = min(NNF_TILE, m_pad - start);
-    for (int u = tid; u < cnt; u += NNF_THREADS) cp_async16(&tile[buf][u], tg + start + u);
+    const int cnt = min(NNF_TILE, m_pad - start) * NNF_FREC;
+    for (int u = tid; u < cnt; u += NNF_THREADS) cp_async16(&tile[buf][u], tg + (size_t)start * NNF_FREC + u);
     cp_async_commit();
   };
+#if NNF_PACKED
+  // query pairs (2 kp, 2 kp + 1) as 64-bit operands, formed once
+  nnf_u64 x2[Q / 2][3];
+#pragma unroll
+  for (int kp = 0; kp < Q / 2; ++kp)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x2[kp][c] = pack2(x[2 * kp][c], x[2 * kp + 1][c]);
+#endif
 
   if (t_begin < t_end) issue_tile(t_begin, 0);
   for (int t = t_begin; t < t_end; ++t) {
@@ -450,7 +495,40 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
       float cm[Q];
 #pragma unroll
       for (int k = 0; k < Q; ++k) cm[k] = INF;
-      const float4* ch = &tile[buf][c * NN_CHUNK];
+      const float4* ch = &tile[buf][c * NN_CHUNK * NNF_FREC];
+#if NNF_PACKED
+#pragma unroll
+      for (int j = 0; j < NN_CHUNK; j += NNF_PIL) {
+        // two broadcast LDS.128 per record deliver its four duplicated components as 64-bit operands
+        nnf_u64 axx[NNF_PIL], ayy[NNF_PIL], azz[NNF_PIL], aww[NNF_PIL];
+        nnf_u64 v2[NNF_PIL][Q / 2];
+#pragma unroll
+        for (int i = 0; i < NNF_PIL; ++i) {
+          const unsigned int addr = (unsigned int)__cvta_generic_to_shared(ch + (j + i) * 2);
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(axx[i]), "=l"(ayy[i]) : "r"(addr));
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(azz[i]), "=l"(aww[i]) : "r"(addr + 16));
+        }
+#pragma unroll
+        for (int i = 0; i < NNF_PIL; ++i) {
+#pragma unroll
+          for (int kp = 0; kp < Q / 2; ++kp) v2[i][kp] = ffma2(x2[kp][2], azz[i], aww[i]);
+#pragma unroll
+          for (int kp = 0; kp < Q / 2; ++kp) v2[i][kp] = ffma2(x2[kp][1], ayy[i], v2[i][kp]);
+#pragma unroll
+          for (int kp = 0; kp < Q / 2; ++kp) v2[i][kp] = ffma2(x2[kp][0], axx[i], v2[i][kp]);
+        }
+#pragma unroll
+        for (int i = 0; i < NNF_PIL; i += 2)
+#pragma unroll
+          for (int kp = 0; kp < Q / 2; ++kp) {
+            float a0, a1, b0, b1;
+            unpack2(v2[i][kp], a0, a1);
+            unpack2(v2[i + 1][kp], b0, b1);
+            cm[2 * kp] = min3(cm[2 * kp], a0, b0);
+            cm[2 * kp + 1] = min3(cm[2 * kp + 1], a1, b1);
+          }
+      }
+#else
 #pragma unroll
       for (int j = 0; j < NN_CHUNK; j += NNF_IL) {
         // one broadcast LDS.128 per record; the record's components sit in the same operand slot of
@@ -498,6 +576,7 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
 #pragma unroll
           for (int k = 0; k < Q; ++k) cm[k] = min3(cm[k], v[i][k], v[i + 1][k]);
       }
+#endif
 #pragma unroll
       for (int k = 0; k < Q; ++k) {
         second[k] = fminf(second[k], fmaxf(cm[k], best[k]));     // smallest minimum among the chunks that are not the best
@@ -567,7 +646,7 @@ constexpr int FBF_Q = 2;
 #ifndef FBF_TILE_RECORDS
 #define FBF_TILE_RECORDS 512
 #endif
-constexpr int FBF_TILE = FBF_TILE_RECORDS;
+constexpr int FBF_TILE = FBF_TILE_RECORDS / NNF_FREC;
 constexpr int FBF_QUEUE = 512;
 
 __global__ void __launch_bounds__(FBF_THREADS)
@@ -576,7 +655,7 @@ nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict_
                           const float* __restrict__ qthr, int qcap, unsigned long long* __restrict__ qkey,
                           const int* __restrict__ stop_flag) {
   if (stop_flag != nullptr && *stop_flag != 0) return;
-  __shared__ __align__(16) float4 tile[2][FBF_TILE];
+  __shared__ __align__(16) float4 tile[2][FBF_TILE * NNF_FREC];
   __shared__ float qx[FBF_THREADS * FBF_Q][3];
   __shared__ int qid[FBF_THREADS * FBF_Q];
   __shared__ int queue[FBF_QUEUE];
@@ -585,7 +664,7 @@ nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict_
   const int split = blockIdx.z;
   const int N = gridDim.y;
   const int nq = (int)min(qcount[b], (unsigned int)qcap);
-  const float4* tg = packed + (size_t)b * m_pad;
+  const float4* tg = packed + (size_t)b * m_pad * NNF_FREC;
   const float4* tg_orig = nn_orig_records(packed, N, m_pad) + (size_t)b * m_pad;
   const float4 ctr = nn_centers(packed, N, m_pad)[b];
   const float INF = Sentinel<float>::inf();
@@ -649,8 +728,8 @@ nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict_
 
     auto issue_tile = [&](int t, int buf) {
       const int start = t * FBF_TILE;
-      const int cnt = min(FBF_TILE, m_pad - start);
-      for (int u = lane; u < cnt; u += FBF_THREADS) cp_async16(&tile[buf][u], tg + start + u);
+      const int cnt = min(FBF_TILE, m_pad - start) * NNF_FREC;
+      for (int u = lane; u < cnt; u += FBF_THREADS) cp_async16(&tile[buf][u], tg + (size_t)start * NNF_FREC + u);
       cp_async_commit();
     };
     int queued = 0;                          // warp-uniform
@@ -666,10 +745,15 @@ nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict_
         float cm[FBF_Q];
 #pragma unroll
         for (int k = 0; k < FBF_Q; ++k) cm[k] = INF;
-        const float4* ch = &tile[buf][c * NN_CHUNK];
+        const float4* ch = &tile[buf][c * NN_CHUNK * NNF_FREC];
 #pragma unroll
         for (int j = 0; j < NN_CHUNK; j += 2) {
+#if NNF_PACKED
+          const float4 p0 = ch[2 * j], p1 = ch[2 * j + 1], p2 = ch[2 * j + 2], p3 = ch[2 * j + 3];
+          const float4 a0 = make_float4(p0.x, p0.z, p1.x, p1.z), a1 = make_float4(p2.x, p2.z, p3.x, p3.z);
+#else
           const float4 a0 = ch[j], a1 = ch[j + 1];
+#endif
 #pragma unroll
           for (int k = 0; k < FBF_Q; ++k) {
             float v0 = __fmaf_rn(x[k][2], a0.z, a0.w), v1 = __fmaf_rn(x[k][2], a1.z, a1.w);
@@ -748,9 +832,15 @@ static NNPlan nn_plan(int N, int n, int m, int elem_size) {
   const int tiles_total = (m_pad + p.tile - 1) / p.tile;
   const long long base = (long long)p.gx * N;
   const long long slots = (long long)device_sm_count() * ctas_per_sm;
-  const long long want = slots * 6;          // >= 6 waves => the short last wave costs a few percent at most
+#ifndef NN_WAVES
+#define NN_WAVES 6
+#endif
+#ifndef NN_MIN_TILES
+#define NN_MIN_TILES 8
+#endif
+  const long long want = slots * NN_WAVES;   // >= 6 waves => the short last wave costs a few percent at most
   long long s = (want + base - 1) / base;
-  const long long max_by_work = tiles_total / 8 > 0 ? tiles_total / 8 : 1;   // >= 8 tiles per CTA keeps prologue/refine overhead small
+  const long long max_by_work = tiles_total / NN_MIN_TILES > 0 ? tiles_total / NN_MIN_TILES : 1;   // >= 8 tiles per CTA keeps prologue/refine overhead small
   const long long fill = (slots + base - 1) / base;                            // but always fill the machine
   if (s > max_by_work) s = max_by_work > fill ? max_by_work : fill;
   if (s > tiles_total) s = tiles_total;

@@ -9,4 +9,4 @@ import bench  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 src, tgt = bench.make_batch(N, 0)
 r, _ = bench.roofline_nn(src.cuda(), tgt.cuda(), bench.peaks())
-print("nn scan call: %.3f ms, %.1f %% algorithmic, %.1f %% executed" % (r["ms_per_launch"], 100 * r["frac"], 100 * r["frac_executed"]))
+print("nn scan call: %.3f ms, %.1f %% executed, %.1f %% algorithmic" % (r["ms_per_launch"], 100 * r["frac"], 100 * r["frac_algorithmic"]))
