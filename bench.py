@@ -355,11 +355,12 @@ def roofline_bwd(src, tgt, pk, with_weight):
     g_src, g_tgt, g_T0 = torch.empty_like(source), torch.empty_like(target), torch.empty((N, 4, 4), device=dev)
     g_w = torch.empty((N, n), device=dev) if with_weight else None
     st = _lib.stream_ptr(dev)
+    ws = torch.empty(lib.dicp_icp_backward_workspace_bytes(N, n, m, 4), dtype=torch.uint8, device=dev)
 
     def launch(k):
         _lib.check(lib.dicp_icp_backward_f32(_lib.ptr(source), _lib.ptr(target), _lib.ptr(w_init) if with_weight else None, None, N, n, m, 6,
                                              ctypes.byref(p), k, _lib.ptr(saved_idx), _lib.ptr(saved_state), _lib.ptr(g_T), None,
-                                             _lib.ptr(g_src), _lib.ptr(g_tgt), _lib.ptr(g_w), _lib.ptr(g_T0), _lib.ptr(ctx.ws), ctx.ws.numel(), st), "bwd")
+                                             _lib.ptr(g_src), _lib.ptr(g_tgt), _lib.ptr(g_w), _lib.ptr(g_T0), _lib.ptr(ws), ws.numel(), st), "bwd")
 
     t10 = time_kernel(lambda: launch(ITERS), reps=5)
     t5 = time_kernel(lambda: launch(ITERS // 2), reps=5)
@@ -574,7 +575,7 @@ def run_ours(args):
                     "api": "pinned host clouds -> H2D (double-buffered on a side stream) -> WeightModel -> dICP.ICP.ICP.icp -> backward to the "
                            "model, the input points and T_init -> all-reduce -> D2H of [loss, dloss/dtheta] and T",
                     "note": "the gradients of the clouds (151 MB) and of the weight model stay on the GPU, where the optimiser of a training "
-                            "loop consumes them; a caller who passes HOST tensors to icp() gets pc / weights copied back lazily (dicp_b200.ICP._Results)"},
+                            "loop consumes them; a caller who passes HOST tensors to icp() gets every result back on the host (plain dict, as upstream)"},
             "gpu_launches": launches_per_step * args.steps,
             "nn_search": "brute (tiled brute-force scan, the north-star kernel)",
             "theta_only": {"value": pairs_total * steps_aux / sec_theta, "unit": "pairs/s", "ms_per_step": 1e3 * sec_theta / steps_aux,

@@ -22,9 +22,10 @@ def _is_empty(x):
 
 
 class _Results(dict):
-    """The result dictionary of `ICP.icp` (ICP.py:294-303).  When the inputs were host tensors the outputs
-    are produced on the GPU; each entry is copied back to the host the first time it is read, so a caller
-    that only wants `T` does not pay for the (N,K,n,1) `weights` history."""
+    """Opt-in (`ICP.lazy_host_results = True`) result dictionary of `ICP.icp` (ICP.py:294-303) for host inputs: the
+    outputs are produced on the GPU and each entry is copied back to the host the first time it is read through
+    `[]`, `get`, `items` or `values`, so a caller that only wants `T` does not pay for the (N,K,n,1) `weights`
+    history.  (Bulk paths of the dict type -- `dict(res)`, `copy`, pickling -- bypass these hooks, hence opt-in.)"""
 
     def _force(self, key):
         v = dict.__getitem__(self, key)
@@ -91,6 +92,9 @@ class ICP:
         self.last_correspondences = None
         # optional YAML key dICP.functionality.svd (commented out upstream, config/dICP_config.yaml:15-16): point-to-point
         # problems are solved by the Kabsch / SVD loop `pt2pt_dICP_SVD` instead of Gauss-Newton
+        # not in the reference: with host inputs, True returns a dict subclass whose large entries (pc, weights, deltas,
+        # costs) are copied back from the GPU on first access instead of eagerly; the default is the plain dict upstream returns
+        self.lazy_host_results = False
         self.use_svd = bool(func.get('svd', False))
         self.svd_literal = False
 
@@ -135,8 +139,9 @@ class ICP:
         else:
             target = target[:, :, :3]
         if self.diff and self.nn.use_gumbel:
-            raise NotImplementedError("the Gumbel-softmax neighbour search (config functionality.gumbel) is "
-                                      "outside the scope of the CUDA solver loop")
+            # config functionality.gumbel ("not yet integrated" upstream, off in the shipped config): soft neighbours
+            # from the streaming Gumbel-softmax kernel, gradients through the softmax; see _gumbel_loop
+            return self._gumbel_loop(source, target, T_init, w_init, trim_dist, loss_fn, dim)
 
         if dim == 2:
             # planar problem: drop z of the points and of the normals (ICP.py:107-116)
@@ -195,6 +200,10 @@ class ICP:
                     "weights": weights.unsqueeze(-1),
                     "stats": {"converged": converged, "iterations": num_iters, "matched_ratio": match_ratio}}
         back = lambda t: t.to(out_dev)      # noqa: E731
+        if not self.lazy_host_results:      # the reference's plain dict of tensors on the input device
+            return {"pc": back(pc), "T": back(T), "costs": back(costs).unsqueeze(-1), "deltas": back(deltas).unsqueeze(-1),
+                    "weights": back(weights).unsqueeze(-1),
+                    "stats": {"converged": back(converged), "iterations": back(num_iters), "matched_ratio": back(match_ratio)}}
         return _Results({
             "pc": _Deferred(lambda: back(pc)),
             "T": back(T),
@@ -203,6 +212,106 @@ class ICP:
             "weights": _Deferred(lambda: back(weights).unsqueeze(-1)),
             "stats": {"converged": back(converged), "iterations": back(num_iters), "matched_ratio": back(match_ratio)},
         })
+
+    def _gumbel_loop(self, source, target, T_init, w_init, trim_dist, loss_fn, dim):
+        """The Gauss-Newton loop (ICP.py:125-303) for `functionality.gumbel: True` with `differentiable=True`: every
+        iteration's neighbours are the Gumbel-softmax soft neighbours of `nn.find_nn` (nn.py:43-70; here the streaming
+        online-softmax kernel `dicp_gumbel_nn_*` with counter-based noise, forward and backward), so correspondences are
+        soft and gradients also flow through the softmax into the moved points -- which the fused hard-correspondence
+        loop does not model.  The per-iteration algebra (residual, trim / robust weights, Jacobian, 6x6 solve, exp-map
+        update, bookkeeping) is batched torch on the GPU with autograd, as upstream; this configuration is off in the
+        shipped config and outside the benchmarked hot path.  Inputs are the normalised batch tensors of `dICP`."""
+        from .loss import loss as _loss
+        dev_in = source.device
+        dev = self._compute_device(dev_in)
+        source, target, T_init, w_init = source.to(dev), target.to(dev), T_init.to(dev), w_init.to(dev)
+        N, n = source.shape[0], source.shape[1]
+        dt = source.dtype
+        pt2pl = self.icp_type == 'pt2pl'
+        if dim == 2:                                                           # ICP.py:107-116
+            zs = source.new_zeros((N, n, 1))
+            source = torch.cat((source[:, :, :2], zs), dim=2)
+            zt = target.new_zeros((N, target.shape[1], 1))
+            target = torch.cat((target[:, :, :2], zt, target[:, :, 3:5], zt), dim=2) if pt2pl else torch.cat((target[:, :, :2], zt), dim=2)
+        steep = self.config['dICP']['parameters']['tanh_steepness']
+        trim = _loss("trim", trim_dist, True, steep) if (trim_dist is not None and trim_dist >= 0.0) else None    # ICP.py:152-155
+        robust = _loss(loss_fn['name'], loss_fn['metric'], True) if loss_fn is not None else None                 # ICP.py:157-160
+        C, r = T_init[:, :3, :3], T_init[:, :3, 3:]
+        P = source.transpose(1, 2)
+        ncols = 3 if dim == 2 else 6
+        reg = 1e-12 * torch.eye(ncols, dtype=dt, device=dev)
+        eye3 = torch.eye(3, dtype=dt, device=dev)
+        converged = torch.zeros(N, dtype=torch.bool, device=dev)
+        num_iters = torch.zeros(N, dtype=dt, device=dev)
+        match_ratio = torch.zeros(N, dtype=dt, device=dev)
+        deltas, weights, costs = [], [], []
+        w = w_init
+        k_run = 0
+        for k in range(self.max_iterations):
+            k_run = k + 1
+            A_pts = C @ P
+            X = (A_pts + r).transpose(1, 2)                                    # ICP.py:137
+            nbr = self.nn.find_nn(X, target)                                   # soft neighbours, (N,n,S)   ICP.py:140
+            e3 = X - nbr[:, :, :3]
+            a = A_pts.transpose(1, 2)
+            if pt2pl:
+                nrm = nbr[:, :, 3:]
+                err = (e3 * nrm).sum(dim=2, keepdim=True)                      # ICP.py:146
+                J = torch.cat((torch.cross(nrm, a, dim=2), -nrm), dim=2)       # ICP.py:172-176
+            else:
+                err = e3
+                z = torch.zeros_like(a[..., 0])
+                hat = torch.stack((z, -a[..., 2], a[..., 1], a[..., 2], z, -a[..., 0], -a[..., 1], a[..., 0], z), dim=-1).reshape(N, n, 3, 3)
+                J = torch.cat((hat.reshape(N, -1, 3), -eye3.repeat(N, n, 1)), dim=2)      # ICP.py:177-180
+            t_w = trim.get_weight(e3) if trim is not None else torch.ones((N, n), dtype=dt, device=dev)
+            l_w = robust.get_weight(err) if robust is not None else torch.ones((N, n), dtype=dt, device=dev)
+            if not pt2pl:                                                      # ICP.py:162-166
+                t_w, l_w = t_w.repeat_interleave(3, dim=1), l_w.repeat_interleave(3, dim=1)
+                err = err.reshape(N, -1, 1)
+            w = w_init * t_w * l_w                                             # ICP.py:169
+            if dim == 2:
+                J = J[:, :, 2:5]                                               # ICP.py:186-189
+            g = torch.sqrt(w + 1.0e-10) - 1.0e-5                               # ICP.py:194
+            err_w, J_w = g.unsqueeze(-1) * err, g.unsqueeze(-1) * J
+            step = -torch.linalg.inv(J_w.transpose(1, 2) @ J_w + reg) @ J_w.transpose(1, 2) @ err_w     # ICP.py:200-201
+            if dim == 2:                                                       # ICP.py:204-207
+                step = torch.cat((step.new_zeros((N, 2, 1)), step, step.new_zeros((N, 1, 1))), dim=1)
+            phi = step[:, 0:3, 0]
+            zz = torch.zeros_like(phi[:, 0])
+            phat = torch.stack((zz, -phi[:, 2], phi[:, 1], phi[:, 2], zz, -phi[:, 0], -phi[:, 1], phi[:, 0], zz), dim=-1).reshape(N, 3, 3)
+            C = torch.matrix_exp(phat).transpose(1, 2) @ C                     # ICP.py:210-214
+            r = r - step[:, 3:6]                                               # ICP.py:216
+            deltas.append(step.detach())
+            w_keep = w.detach()
+            if weights:                                                        # ICP.py:224-226
+                w_keep = torch.where((w_keep.sum(dim=1) == 0.0).unsqueeze(-1), weights[-1].squeeze(-1), w_keep)
+            weights.append(w_keep.unsqueeze(-1))
+            cost = (err_w.transpose(1, 2) @ err_w).detach()                    # ICP.py:229
+            if costs:
+                cost = torch.where(cost == 0.0, costs[-1], cost)
+            costs.append(cost)
+            below = torch.linalg.norm(step, dim=1).detach().squeeze(-1) < self.tolerance    # ICP.py:237
+            converged = converged | below
+            if bool(below.any()) and not self.const_iter:                      # ICP.py:240-260
+                num_iters = torch.where(below & (num_iters == 0), torch.full_like(num_iters, k + 1), num_iters)
+                matched = (w > self.match_ratio_thresh).sum(dim=1)
+                start = (w_init > self.match_ratio_thresh).sum(dim=1)
+                start = torch.where(start == 0, torch.ones_like(start), start)
+                match_ratio = torch.where(below & (match_ratio == 0), match_ratio + matched / start, match_ratio)
+                w_init = w_init * (~below).to(dt).unsqueeze(-1)
+                if bool(below.all()):
+                    break
+        num_iters = torch.where(num_iters == 0, torch.full_like(num_iters, k_run), num_iters)   # ICP.py:267-271
+        matched = (w > self.match_ratio_thresh).sum(dim=1)
+        start = (w_init > self.match_ratio_thresh).sum(dim=1)
+        start = torch.where(start == 0, torch.ones_like(start), start)
+        match_ratio = torch.where(match_ratio == 0, (matched / start).to(dt), match_ratio)
+        pc = (C @ P + r).transpose(1, 2)                                       # ICP.py:274
+        T = torch.cat((torch.cat((C, r), dim=2), torch.tensor([[[0.0, 0.0, 0.0, 1.0]]], dtype=dt, device=dev).repeat(N, 1, 1)), dim=1)
+        back = (lambda t: t) if dev_in == dev else (lambda t: t.to(dev_in))
+        return {"pc": back(pc), "T": back(T), "costs": back(torch.stack(costs, dim=1).squeeze(-1)),
+                "deltas": back(torch.stack(deltas, dim=1)), "weights": back(torch.stack(weights, dim=1)),
+                "stats": {"converged": back(converged), "iterations": back(num_iters), "matched_ratio": back(match_ratio)}}
 
     def _compute_device(self, input_device):
         _functions.require_cuda()

@@ -303,9 +303,15 @@ class ICPFunction(torch.autograd.Function):
         ctx.dims = (N, n, m, S)
         ctx.has_w = w_init is not None
         ctx.n_valid = n_valid
+        del ws                                    # the reverse pass allocates its own, much smaller workspace
+        if k_run < K:
+            # early stop: the history buffers were sized for max_iterations; keep only the iterations that ran (with the
+            # default max_iterations = 100 and a handful of iterations this is the difference between 1.6 GB and 0.1 GB
+            # each for `weights` and the saved correspondences of a 256 x 16k batch)
+            deltas, weights, costs = deltas[:, :k_run].clone(), weights[:, :k_run].clone(), costs[:, :k_run].clone()
+            saved_idx, saved_state = saved_idx[:k_run].clone(), saved_state[:k_run + 1].clone()
         ctx.save_for_backward(source, target, w_init if w_init is not None else source.new_empty(0),
                               saved_idx, saved_state)
-        ctx.ws = ws
         if keep_idx is not None:                 # the caller asked for the correspondences (ICP.keep_correspondences)
             keep_idx.append(saved_idx[:k_run])
         outs = (pc, T, deltas[:, :k_run], weights[:, :k_run], costs[:, :k_run], converged.bool(), num_iters, match_ratio)
@@ -326,7 +332,7 @@ class ICPFunction(torch.autograd.Function):
         g_tgt = torch.empty_like(target)
         g_w = torch.empty((N, n), dtype=dt, device=dev) if (ctx.has_w and ctx.needs_input_grad[3]) else None
         g_T0 = torch.empty((N, 4, 4), dtype=dt, device=dev)
-        ws = ctx.ws
+        ws = _workspace(lib.dicp_icp_backward_workspace_bytes(N, n, m, source.element_size()), dev)
         with torch.cuda.device(dev):
             rc = getattr(lib, "dicp_icp_backward_" + sfx)(
                 ptr(source), ptr(target), ptr(w_init) if ctx.has_w else None, ptr(ctx.n_valid), N, n, m, S, ctypes.byref(ctx.params), ctx.k_run,

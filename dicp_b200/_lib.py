@@ -42,6 +42,7 @@ _SIGNATURES = {
     "dicp_last_error": ([], ctypes.c_char_p),
     "dicp_nn_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),
+    "dicp_icp_backward_workspace_bytes": ([_I, _I, _I, _I], _Z),
     "dicp_nn_packed_bytes": ([_I, _I, _I], _Z),
     "dicp_kabsch_workspace_bytes": ([_I, _I], _Z),
     "dicp_kabsch_icp_workspace_bytes": ([_I, _I, _I, _I], _Z),

@@ -499,12 +499,12 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
   DICP_CHECK_ARG(N >= 1 && N <= 65535 && n >= 1 && m >= 1 && (S == 3 || S == 6), "bad sizes");
   DICP_CHECK_ARG(p->icp_type != DICP_PT2PL || S == 6, "pt2pl needs a 6-column target");
   DICP_CHECK_ARG(iters_run >= 1 && iters_run <= p->max_iterations, "iters_run out of range");
-  if (ws == nullptr || ws_bytes < plan_workspace(nullptr, 0, N, n, m, sizeof(T)).total) {
+  if (ws == nullptr || ws_bytes < plan_workspace(nullptr, 0, N, n, m, sizeof(T), true).total) {
     set_error("dicp_icp_backward: workspace too small");
     return DICP_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T));
+  IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T), true);
   const WeightParams P = make_weight_params(p);
   const bool fast = weight_params_fast(P);
   const TilePlan plan = bw_tile_plan(N, n);

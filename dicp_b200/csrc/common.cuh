@@ -223,6 +223,6 @@ struct IcpWorkspace {
   void* gtab;          // fp32: [N, m] aligned gradient records of the targets (backward scatter); unused for fp64
   size_t total;
 };
-IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size);
+IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size, bool backward_only);
 
 }  // namespace dicp

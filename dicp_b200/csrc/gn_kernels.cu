@@ -651,20 +651,22 @@ finalize_kernel(const T* __restrict__ source, int n, const double* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // workspace layout of one forward / backward call
 // ---------------------------------------------------------------------------------------
-IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size) {
+IcpWorkspace plan_workspace(void* ws, size_t ws_bytes, int N, int n, int m, int elem_size, bool backward_only) {
   Arena ar(ws, ws_bytes);
   IcpWorkspace w;
-  w.packed = ar.take<char>(nn_packed_bytes(N, m, elem_size));
-  w.nn_ws_bytes = nn_search_ws_bytes(N, n, m, elem_size);
+  // the reverse pass needs none of the search structures: its workspace is a fraction of the forward's, so the caller
+  // can drop the forward workspace as soon as the forward call returns
+  w.packed = ar.take<char>(backward_only ? 1 : nn_packed_bytes(N, m, elem_size));
+  w.nn_ws_bytes = backward_only ? 0 : nn_search_ws_bytes(N, n, m, elem_size);
   w.nn_ws = ar.take<char>(w.nn_ws_bytes > 0 ? w.nn_ws_bytes : 1);
-  w.partials = ar.take<double>((size_t)N * gn_blocks_per_pair(N, n) * RED_N);
+  w.partials = ar.take<double>(backward_only ? 1 : (size_t)N * gn_blocks_per_pair(N, n) * RED_N);
   w.ctrl = ar.take<Ctrl>(1);
-  w.bw_state = ar.take<double>((size_t)N * BW_STRIDE);
-  w.bw_partials = ar.take<double>((size_t)N * bw_rows_per_pair(N, n) * BW_NRED);
-  w.grid_ws_bytes = grid_ws_layout(nullptr, 0, N, n, m, elem_size).total;
-  w.grid_ws = ar.take<char>(w.grid_ws_bytes);
+  w.bw_state = ar.take<double>(backward_only ? (size_t)N * BW_STRIDE : 1);
+  w.bw_partials = ar.take<double>(backward_only ? (size_t)N * bw_rows_per_pair(N, n) * BW_NRED : 1);
+  w.grid_ws_bytes = backward_only ? 0 : grid_ws_layout(nullptr, 0, N, n, m, elem_size).total;
+  w.grid_ws = ar.take<char>(w.grid_ws_bytes > 0 ? w.grid_ws_bytes : 1);
   w.rows = ar.take<char>(gn_rows_bytes(N, m, elem_size) > 0 ? gn_rows_bytes(N, m, elem_size) : 1);
-  w.gtab = ar.take<char>(bw_gtab_bytes(N, m, elem_size) > 0 ? bw_gtab_bytes(N, m, elem_size) : 1);
+  w.gtab = ar.take<char>(backward_only && bw_gtab_bytes(N, m, elem_size) > 0 ? bw_gtab_bytes(N, m, elem_size) : 1);
   w.total = ar.off;
   return w;
 }
@@ -685,13 +687,13 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   DICP_CHECK_ARG(p->loss_id >= 0 && p->loss_id <= 2, "invalid loss id");                 // loss.py:19
   DICP_CHECK_ARG(p->max_iterations >= 1, "max_iterations must be >= 1");
   DICP_CHECK_ARG(hook != nullptr || p->nn_mode == DICP_NN_BRUTE || p->nn_mode == DICP_NN_GRID, "invalid nn_mode");
-  if (ws == nullptr || ws_bytes < plan_workspace(nullptr, 0, N, n, m, sizeof(T)).total) {
+  if (ws == nullptr || ws_bytes < plan_workspace(nullptr, 0, N, n, m, sizeof(T), false).total) {
     set_error("dicp_icp_forward: workspace too small");
     return DICP_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
   typedef typename Vec4<T>::type V4;
-  IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T));
+  IcpWorkspace w = plan_workspace(ws, ws_bytes, N, n, m, sizeof(T), false);
   const int K = p->max_iterations;
   const bool pl = p->icp_type == DICP_PT2PL;
   const long long nw = (long long)n * (pl ? 1 : 3);
@@ -824,7 +826,10 @@ int dicp_version(void) { return DICP_VERSION; }
 const char* dicp_last_error(void) { return dicp::g_err; }
 
 size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size) {
-  return dicp::plan_workspace(nullptr, 0, N, n, m, elem_size).total;
+  return dicp::plan_workspace(nullptr, 0, N, n, m, elem_size, false).total;
+}
+size_t dicp_icp_backward_workspace_bytes(int N, int n, int m, int elem_size) {
+  return dicp::plan_workspace(nullptr, 0, N, n, m, elem_size, true).total;
 }
 
 int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init, const int32_t* m_valid, const int32_t* n_valid,

@@ -204,7 +204,10 @@ DICP_API int dicp_icp_forward_hooked_f64(const double* source, const double* tar
 /* ---- reverse pass: replaces torch autograd through ICP.py:132-280 -----
  * grad_T [N,4,4], grad_pc [N,n,3] (either may be NULL == zero)
  * grad_source [N,n,3], grad_target [N,m,S], grad_w [N,n] (may be NULL), grad_T_init [N,4,4]
- * are overwritten.  iters_run is the value the forward returned.                        */
+ * are overwritten.  iters_run is the value the forward returned.  The workspace is sized by
+ * dicp_icp_backward_workspace_bytes (no search structures: a fraction of the forward's, which the
+ * caller may free as soon as the forward call has returned).                              */
+DICP_API size_t dicp_icp_backward_workspace_bytes(int N, int n, int m, int elem_size);
 DICP_API int dicp_icp_backward_f32(const float* source, const float* target, const float* w_init, const int32_t* n_valid,
                           int N, int n, int m, int S, const dicp_params* params, int iters_run,
                           const int32_t* saved_idx, const double* saved_state,

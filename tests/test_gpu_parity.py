@@ -817,6 +817,37 @@ def test_gumbel_nn_matches_formula_on_its_own_noise(dtype, tol, S):
     assert abs(G.mean().item() - 0.5772) < 0.02 and abs(G.var().item() - 1.6449) < 0.06
 
 
+@pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
+def test_icp_loop_with_gumbel_config_runs_and_approaches_the_hard_loop(icp_type, tmp_path):
+    """config functionality.gumbel: True with differentiable=True (rejected in round 1): the loop runs on the soft neighbours
+    of the streaming Gumbel-softmax kernel; with a small temperature they are the hard neighbours up to exp(-gap / tau),
+    so the transform must approach the fused hard-correspondence loop's, and gradients must reach source and target."""
+    import yaml
+    from dICP.ICP import ICP
+    from oracle.dicp_oracle import make_wavy_pair
+    with open(os.path.join(ROOT, "config", "dICP_config.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["dICP"]["functionality"]["gumbel"] = True
+    cfg["dICP"]["functionality"]["gumbel_tau"] = 1.0e-4
+    cfg["dICP"]["parameters"]["const_iter"] = True
+    path = tmp_path / "gumbel.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    src, tgt = make_wavy_pair(2, 400, 500, seed=12, dtype=torch.float64, noise=0.0, with_normals=icp_type == "pt2pl")
+    soft = ICP(config_path=str(path), icp_type=icp_type, max_iterations=4, tolerance=1e-12, differentiable=True)
+    hard = _icp(icp_type, True, 4, 1e-12, const_iter=True)
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    T0 = torch.eye(4, dtype=torch.float64, device="cuda").repeat(2, 1, 1)
+    kw = dict(trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+    torch.manual_seed(0)
+    res = soft.icp(s, t, T0, **kw)
+    ref = hard.icp(src.cuda(), tgt.cuda(), T0, **kw)
+    assert res["T"].shape == (2, 4, 4) and res["deltas"].shape == (2, 4, 6, 1) and res["weights"].shape[1] == 4
+    assert rel_err(res["T"].detach().cpu(), ref["T"].cpu()) < 5e-3
+    res["T"].sum().backward()
+    assert torch.isfinite(s.grad).all() and torch.isfinite(t.grad).all() and float(s.grad.abs().sum()) > 0 and float(t.grad.abs().sum()) > 0
+
+
 def test_gumbel_nn_default_constructor_reference_test():
     """tests/test_nn.py:12-41 verbatim semantics: default nn() is the Gumbel path; tau = 0.1 makes the
     soft neighbour equal the hard one on this point set; gradients reach query and points."""
