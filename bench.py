@@ -114,6 +114,33 @@ def learning_loss(res, theta):
     return (res["T"][:, :3, :].reshape(-1, 12) * theta).sum()
 
 
+class _PointLinear(torch.autograd.Function):
+    """y = x @ w + b over millions of points.  torch's own backward computes grad_w = x^T g as ONE GEMM with K = all points,
+    for which cuBLAS picks a SIMT kernel that takes 1 ms at 4 M points; here the reduction over the points is split into
+    chunks of 4096 (a batched GEMM) and summed, which takes 0.1 ms.  need_gx: whether a gradient w.r.t. x is wanted."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, need_gx):
+        ctx.save_for_backward(x, w)
+        ctx.need_gx = need_gx
+        return x @ w + b
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        x2, g2 = x.reshape(-1, x.shape[-1]), g.reshape(-1, g.shape[-1])
+        M = x2.shape[0]
+        chunk = 4096
+        main = (M // chunk) * chunk
+        gw = x2.new_zeros((x2.shape[1], g2.shape[1]))
+        if main:
+            gw = gw + torch.bmm(x2[:main].reshape(-1, chunk, x2.shape[1]).transpose(1, 2), g2[:main].reshape(-1, chunk, g2.shape[1])).sum(0)
+        if main < M:
+            gw = gw + x2[main:].t() @ g2[main:]
+        gx = (g @ w.t()) if ctx.need_gx else None
+        return gx, gw, g2.sum(0), None
+
+
 class WeightModel(torch.nn.Module):
     """The learnable part of learning mode: a per-point prior weight for `weight=`,
         w_i = sigmoid(MLP(p_i / extent) + table[voxel(p_i)] + 2),
@@ -133,7 +160,8 @@ class WeightModel(torch.nn.Module):
 
     def forward(self, pts):
         x = pts / self.extent
-        logit = (torch.tanh(x @ self.w1 + self.b1) @ self.w2 + self.b2).squeeze(-1)
+        h = torch.tanh(_PointLinear.apply(x, self.w1, self.b1, False))
+        logit = _PointLinear.apply(h, self.w2, self.b2, True).squeeze(-1)
         cell = ((x * 0.5 + 0.5).clamp(0.0, 1.0 - 1e-6) * self.grid).long()
         lin = (cell[..., 0] * self.grid + cell[..., 1]) * self.grid + cell[..., 2]
         # index_select: its backward is an atomic index_add_ (the sort-based backward of advanced indexing costs 1 ms here)
@@ -301,7 +329,7 @@ def roofline_nn(src, tgt, pk):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of this round's kernels at the C3
 # shape (profiles/r02_ncu_top_kernels.md); other shapes have no capture -> null
-NCU_TRAFFIC = {("nn", 256, 16384, 16384): 201.7e6, ("gn", 256, 16384, 16384): 229.6e6, ("bwd", 256, 16384, 16384): 523.8e6}
+NCU_TRAFFIC = {("nn", 256, 16384, 16384): 199.7e6, ("gn", 256, 16384, 16384): 229.6e6, ("bwd112", 256, 16384, 16384): 521.7e6}
 
 
 def roofline_gn(src, tgt, idx, pk):
@@ -370,7 +398,8 @@ def roofline_bwd(src, tgt, pk, with_weight):
     nbytes = per * N * n
     ach = nbytes / sec / 1e9
     return {"kernel": "bwd_points_staged_kernel<pt2pl> + bwd_pair_kernel, one reverse iteration", "bound": "hbm", "achieved": ach,
-            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC.get(("bwd", N, n, m)),
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "traffic": None if with_weight else NCU_TRAFFIC.get(("bwd112", N, n, m)),      # the capture is of the loop without a prior weight
             "ms_per_launch": sec * 1e3, "bytes_per_correspondence": per, "with_weight_gradient": with_weight, "units_per_launch": float(N) * n, "pairs": N,
             "whole_backward_ms": t10 * 1e3, "peak_source": pk["source"]}
 
@@ -537,7 +566,7 @@ def run_ours(args):
         del big_src, big_tgt
         roof_bwd = roofline_bwd(src_d.detach(), tgt_d.detach(), pk, True)
         roof_bwd["without_weight_gradient"] = {k: v for k, v in roofline_bwd(src_d.detach(), tgt_d.detach(), pk, False).items()
-                                               if k in keep + ("bytes_per_correspondence",)}
+                                               if k in keep + ("bytes_per_correspondence", "traffic")}
         mid = 4
         roof_bwd["at_%d_pairs" % (mid * PAIRS_PER_GPU)] = {
             k: v for k, v in roofline_bwd(src_d.detach().repeat(mid, 1, 1), tgt_d.detach().repeat(mid, 1, 1), pk, True).items() if k in keep}
