@@ -542,11 +542,8 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
       if constexpr (sizeof(T) == 4) {
 #define DICP_BW_LAUNCH(PL, FW)                                                                                                     \
   do {                                                                                                                             \
-    static bool attr_set = false;                                                                                                  \
-    if (!attr_set) {                                                                                                               \
+    if (smem > 48 * 1024)                                                                                                          \
       DICP_CUDA(cudaFuncSetAttribute(bwd_points_staged_kernel<PL, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-      attr_set = true;                                                                                                             \
-    }                                                                                                                              \
     bwd_points_staged_kernel<PL, FW><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
                                                                          grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w, w.bw_partials, nrows, plan, S, n_valid); \
   } while (0)

@@ -489,11 +489,8 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
       constexpr size_t smem = (size_t)GN_STAGES * GN_TILE * 20 + (GN_THREADS / 32) * (32 + 16) * sizeof(double) + 2 * GN_STAGES * sizeof(uint64_t);
 #define DICP_GN_LAUNCH1(PL, DM, FW)                                                                                                \
   do {                                                                                                                             \
-    static bool attr_set = false;     /* idempotent: a race only repeats the call */                                               \
-    if (!attr_set) {                                                                                                               \
+    if (smem > 48 * 1024)             /* per device and cheap: no cached flag (a process may drive several devices) */             \
       DICP_CUDA(cudaFuncSetAttribute(gn_accum_staged_kernel<PL, DM, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_set = true;                                                                                                             \
-    }                                                                                                                              \
     gn_accum_staged_kernel<PL, DM, FW><<<dim3(plan.ctas, 1, 1), GN_THREADS, smem, st>>>(                                            \
         source, target, (pl && rows24) ? nullptr : rows, w_init, idx, state, n, m, P, weights_out, w_pair_stride, partials, plan,  \
         stop_flag, N, n_valid);                                                                                                    \
