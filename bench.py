@@ -321,15 +321,31 @@ def roofline_nn(src, tgt, pk):
             "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
             "achieved_algorithmic": algorithmic, "frac_algorithmic": algorithmic / peak,
             "peak_measured_ffma": probe, "frac_of_measured_ffma_peak": executed / probe if probe else None,
-            "traffic": NCU_TRAFFIC.get(("nn", N, n, m)), "ms_per_launch": sec * 1e3,
+            "traffic": ncu_traffic("nn_scan", (N, n, m)), "ms_per_launch": sec * 1e3,
             "peak_source": "nominal: %d SMs x 128 lanes x 2 x sm_max_mhz (%s; MEASURED_PEAKS.json has no FP32 CUDA-core figure); "
                            "peak_measured_ffma: independent FFMA chains timed in this run" % (sms, pk["source"]),
             "flop_per_pair_eval": {"algorithmic": 8, "executed": 6}, "units_per_launch": evals}, idx
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of this round's kernels at the C3
-# shape (profiles/r02_ncu_top_kernels.md); other shapes have no capture -> null
-NCU_TRAFFIC = {("nn", 256, 16384, 16384): 199.7e6, ("gn", 256, 16384, 16384): 229.6e6, ("bwd112", 256, 16384, 16384): 521.7e6}
+def ncu_traffic(kernel, shape):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, read from the committed summary of this
+    build's `ncu --set full` captures of exactly the launches the probes below time (profiles/r02_ncu_probe_kernels.md, made by
+    tools/ncu_summary.py from the .ncu-rep files; C3 shape only) -- null for any other shape or when the file is missing."""
+    if tuple(shape) != (256, 16384, 16384):
+        return None
+    path = os.path.join(ROOT, "profiles", "r02_ncu_probe_kernels.md")
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, inside = 0.0, False
+    with open(path) as f:
+        for line in f:
+            if line.startswith("## "):
+                inside = line[3:].strip() == kernel
+            elif inside and line.startswith("| dram__bytes_"):
+                cells = [c.strip() for c in line.strip().strip("|").split("|")]
+                total += float(cells[1]) * unit.get(cells[2], 1.0)
+    return total or None
 
 
 def roofline_gn(src, tgt, idx, pk):
@@ -357,7 +373,7 @@ def roofline_gn(src, tgt, idx, pk):
     ach = nbytes / sec / 1e9
     return {"kernel": "gn_accum_staged_kernel<pt2pl,3> (one dicp_gn_accumulate_f32 call = the loop's single launch)", "bound": "hbm",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "traffic": NCU_TRAFFIC.get(("gn", N, n, m)),
+            "traffic": ncu_traffic("gn_accumulate", (N, n, m)),
             "ms_per_launch": sec * 1e3, "peak_source": pk["source"], "bytes_per_correspondence": 48,
             "units_per_launch": float(N) * n, "pairs": N}
 
@@ -399,7 +415,7 @@ def roofline_bwd(src, tgt, pk, with_weight):
     ach = nbytes / sec / 1e9
     return {"kernel": "bwd_points_staged_kernel<pt2pl> + bwd_pair_kernel, one reverse iteration", "bound": "hbm", "achieved": ach,
             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "traffic": None if with_weight else NCU_TRAFFIC.get(("bwd112", N, n, m)),      # the capture is of the loop without a prior weight
+            "traffic": ncu_traffic("bwd_points_124B" if with_weight else "bwd_points_112B", (N, n, m)),
             "ms_per_launch": sec * 1e3, "bytes_per_correspondence": per, "with_weight_gradient": with_weight, "units_per_launch": float(N) * n, "pairs": N,
             "whole_backward_ms": t10 * 1e3, "peak_source": pk["source"]}
 
