@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdicp_b200.so")
 SOURCES = ["nn_kernels.cu", "gn_kernels.cu", "bwd_kernels.cu", "kabsch_kernels.cu", "grid_nn_kernels.cu", "gumbel_kernels.cu"]
-HEADERS = ["common.cuh", "dicp_math.cuh", os.path.join("..", "..", "include", "dicp_b200.h")]
+HEADERS = ["common.cuh", "dicp_math.cuh", "tile_stream.cuh", os.path.join("..", "..", "include", "dicp_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false"]

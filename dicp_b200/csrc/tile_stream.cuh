@@ -38,11 +38,12 @@ struct TilePlan {
 };
 
 // number of chunk starts in [0, x]
-#if !defined(__CUDACC__)
-#define __host__
-#define __device__
+#if defined(__CUDACC__)
+#define DICP_TS_HD __host__ __device__ __forceinline__
+#else
+#define DICP_TS_HD inline
 #endif
-__host__ __device__ inline long long tp_bounds(const TilePlan& p, long long x) {
+DICP_TS_HD long long tp_bounds(const TilePlan& p, long long x) {
   return x < p.full ? x / p.k + 1 : p.full / p.k + (x - p.full) / p.k_last + 1;
 }
 
@@ -71,12 +72,6 @@ inline TilePlan make_tile_plan(int N, int n, int tile, int ctas_per_sm, int k) {
   p.rows = (int)rows;
   return p;
 }
-
-#if defined(__CUDACC__)
-#define DICP_TS_HD __host__ __device__ __forceinline__
-#else
-#define DICP_TS_HD inline
-#endif
 
 // Walks the tiles of one CTA in schedule order without a division per tile or per chunk: the chunk starts of the
 // full waves advance by a constant (adv_b pairs, adv_j tiles), the one chunk of the final wave is located once per
