@@ -33,7 +33,7 @@ extern "C" {
 #define DICP_API
 #endif
 
-#define DICP_VERSION 100
+#define DICP_VERSION 200
 
 #define DICP_ERR_ARG       -1   /* bad size / null pointer / unsupported option */
 #define DICP_ERR_WORKSPACE -2   /* workspace too small */
