@@ -498,6 +498,7 @@ def run_ours(args):
             if i + 1 < steps:
                 enqueue_copy(slots[(i + 1) % 2])
             cur.wait_event(sl["ready"])
+            sl["src"].grad = sl["tgt"].grad = None
             s = sl["src"].requires_grad_(True)
             t = sl["tgt"].requires_grad_(True)
             loss, res = learning_step(s, t, sl["T0"])
