@@ -140,10 +140,13 @@ __device__ __forceinline__ void gn_enter_segment(GnPairCtx<T>& ctx, int b, long 
 // transaction bytes) and an "empty" mbarrier (one arrival per warp) per stage.  No __syncthreads separates
 // tiles: every warp waits for a stage on its own, releases it on its own, and the warp whose turn it is (tile L
 // is fed by warp L % WARPS) refills the stage that was released one step earlier, so the warps of a CTA drift by up
-// to a tile and their memory waits and arithmetic interleave instead of lining up (12 loosely coupled streams
-// per SM instead of 3 lock-stepped CTAs).  Lane l of warp w owns correspondences [U (32 w + l), +U) of the tile:
-// its indices / prior weights are one LDS.128, its points three, its weights row one STG.128.  The (C, r, active)
-// record of the next segment's pair is fetched one step ahead with cp.async into a per-warp slot.
+// to a tile and their memory waits and arithmetic interleave instead of lining up (16 loosely coupled streams
+// per SM instead of 4 lock-stepped CTAs).  Lane l of warp w owns correspondences [U (32 w + l), +U) of the tile
+// (U = 2: 256-correspondence tiles): its indices / prior weights / weights row are one 8-byte access each, its points
+// three.  The (C, r, active) record of the next segment's pair is fetched one step ahead with cp.async into a
+// per-warp slot.  The rows are gathered with ONE request each (LDG.256 on the aligned table): every variant with two
+// requests per row (24-byte rows, cp.async into shared memory) measured slower -- the gather is bound by the request
+// rate through L1 / L2, not by registers or DRAM bytes.
 // ---------------------------------------------------------------------------------------------------------
 template <bool PT2PL, int DIM, bool FASTW>
 __global__ void __launch_bounds__(GN_THREADS, GN_MINB)
