@@ -1,11 +1,14 @@
-// kabsch_kernels.cu — the per-point half of the Kabsch / SVD point-to-point step
-// (ICP.py:557-563): centroids of the source points and of their nearest neighbours and the
-// 3x3 cross-covariance, as ONE fused pass over the correspondences:
-//   sums[b] = ( sum p , sum q , sum q p^T ),   q_i = target[b, idx[b,i], :3]
-// from which  p_mean = Sp/n, q_mean = Sq/n, W = M/n - q_mean p_mean^T  (host side, 3x3).
-// HBM bound: 12 (p) + 4 (idx) + 12 (gathered q) = 28 B per correspondence.  The 3x3 SVD, the
-// determinant fix and the composition (ICP.py:566-578) are O(1) per pair and stay in torch.
-// The adjoint kernel gives autograd the gradients to the points and (scatter-add) to the target.
+// kabsch_kernels.cu — the Kabsch / SVD point-to-point path (ICP.py:533-591).
+//
+// Stage kernels (dicp_kabsch_sums_*): centroids of the (moved) source points and of their nearest neighbours and the
+// 3x3 cross-covariance as ONE fused pass over the correspondences (ICP.py:557-563):
+//   sums[b] = ( sum x , sum q , sum q x^T ),   q_i = target[b, idx[b,i], :3],  x_i = C_a p_i + r_a
+// from which  x_mean = Sx/n, q_mean = Sq/n, W = M/n - q_mean x_mean^T.  HBM bound: 12 (p) + 4 (idx) + 12 (gathered q) =
+// 28 B per correspondence.  Their adjoint scatter-adds into the target.
+//
+// The whole loop (dicp_kabsch_icp_forward_* / _backward_*, second half of this file): search, sums, one thread per pair
+// for the 3x3 SVD + determinant fix + composition (kabsch_step in dicp_math.cuh), device-side convergence test, and the
+// hand-written reverse pass through the saved correspondences and per-iteration records.
 #include "common.cuh"
 
 namespace dicp {
