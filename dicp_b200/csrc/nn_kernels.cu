@@ -642,7 +642,11 @@ nn_scan_f32_kernel(const float* __restrict__ q, const double* __restrict__ state
 // 64-bit atomicMin on (d2 bits, index): the lexicographic first minimum, as torch.argmin.  Typically 2-3
 // chunks per query are candidates, so this costs half of an exact rescan of all targets.
 constexpr int FBF_THREADS = 32;
-constexpr int FBF_Q = 2;
+#ifndef FBF_QPL
+#define FBF_QPL 2
+#endif
+constexpr int FBF_Q = FBF_QPL;          // listed queries per lane and pass
+constexpr int FBF_SLOT_BITS = 8;        // queue entries: (chunk << 8) | query slot
 #ifndef FBF_TILE_RECORDS
 #define FBF_TILE_RECORDS 512
 #endif
@@ -678,7 +682,7 @@ nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict_
     __syncwarp();
     for (int t = lane; t < count; t += FBF_THREADS) {
       const int e = queue[t];
-      const int slot = e & (FBF_THREADS * FBF_Q - 1), chunk = e >> 6;
+      const int slot = e & ((1 << FBF_SLOT_BITS) - 1), chunk = e >> FBF_SLOT_BITS;
       const float x0 = qx[slot][0], x1 = qx[slot][1], x2 = qx[slot][2];
       const float4* ch = tg_orig + (size_t)chunk * NN_CHUNK;
       float bd = INF;
@@ -693,7 +697,7 @@ nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict_
     }
     __syncwarp();
   };
-  static_assert(FBF_THREADS * FBF_Q == 64, "queue entries keep the query slot in 6 bits");
+  static_assert(FBF_THREADS * FBF_Q <= (1 << FBF_SLOT_BITS), "queue entries keep the query slot in FBF_SLOT_BITS bits");
 
   for (int qblk = blockIdx.x * (FBF_THREADS * FBF_Q); qblk < nq; qblk += gridDim.x * (FBF_THREADS * FBF_Q)) {
     float x[FBF_Q][3], thr[FBF_Q];
@@ -768,7 +772,7 @@ nn_fallback_filter_kernel(const float* __restrict__ q, const double* __restrict_
           const bool hit = !(cm[k] > thr[k]);
           const unsigned int mask = __ballot_sync(0xffffffffu, hit);
           if (mask != 0u) {
-            if (hit) queue[queued + __popc(mask & ((1u << lane) - 1u))] = (chunk << 6) | (k * FBF_THREADS + lane);
+            if (hit) queue[queued + __popc(mask & ((1u << lane) - 1u))] = (chunk << FBF_SLOT_BITS) | (k * FBF_THREADS + lane);
             queued += __popc(mask);
             if (queued > FBF_QUEUE - FBF_THREADS) { flush(queued); queued = 0; }
           }
@@ -914,7 +918,10 @@ static int launch_fallback(const NNWorkspace& w, int N, cudaStream_t st, const f
   // there are many pairs (empty CTAs are not free), enough to fill the machine when there are few.
   const int gx_cap = (w.fb_cap + FBF_THREADS * FBF_Q - 1) / (FBF_THREADS * FBF_Q);
   int gx = (device_sm_count() * 8 + N * fs - 1) / (N * fs);
-  if (gx < 4) gx = 4;
+#ifndef NN_FB_MIN_GX
+#define NN_FB_MIN_GX 4
+#endif
+  if (gx < NN_FB_MIN_GX) gx = NN_FB_MIN_GX;
   if (gx > gx_cap) gx = gx_cap;
   dim3 grid(gx, N, fs);
   nn_fallback_filter_kernel<<<grid, FBF_THREADS, 0, st>>>(q, state, packed, n, m_pad, tps, w.fb_count, w.fb_list, w.fb_thr, w.fb_cap, w.fb_key, stop_flag);
