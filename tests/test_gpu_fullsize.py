@@ -242,3 +242,81 @@ def test_tile_ring_edge_shapes_vs_oracle(N, n, icp_type):
     assert rel_err(t.grad[pairs].cpu(), t64.grad) < 5e-4
     assert rel_err(w.grad[pairs].cpu(), w64.grad) < 5e-4
     assert rel_err(T0.grad[pairs].cpu(), T64.grad) < 5e-4
+
+
+@pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
+def test_planar_problem_through_the_staged_fp32_kernels(icp_type):
+    """dim = 2 (ICP.py:107-116, 186-189, 204-207) with n % 4 == 0 in fp32: the DIM = 2 instantiations of the staged
+    accumulate / reverse kernels (the reference's own planar fixture has 65 points and takes the generic path)."""
+    from oracle.dicp_oracle import IcpSettings, icp_forward
+    N, n, m, K = 3, 600, 900, 5
+    gen = torch.Generator().manual_seed(21)
+    # outline of a 10 m x 6 m room with a bump on every wall: rotation and translation are both well observable in the plane
+    side = torch.randint(0, 4, (N, m), generator=gen)
+    u = torch.rand((N, m), generator=gen, dtype=torch.float64) * 2.0 - 1.0
+    bump = 0.3 * torch.sin(4.0 * u)
+    dbump = 1.2 * torch.cos(4.0 * u)
+    horiz = side < 2
+    sgn = torch.where(side % 2 == 0, 1.0, -1.0).double()
+    x = torch.where(horiz, 5.0 * u, sgn * (5.0 + bump))
+    y = torch.where(horiz, sgn * (3.0 + bump), 3.0 * u)
+    # outward normal of the curve: horizontal walls y = s (3 + bump(u)), x = 5 u -> (-s dbump / 5, 1) s ; vertical alike
+    nx = torch.where(horiz, -dbump / 5.0, torch.ones_like(u)) * torch.where(horiz, torch.ones_like(u), sgn)
+    ny = torch.where(horiz, torch.ones_like(u), -dbump / 3.0) * torch.where(horiz, sgn, torch.ones_like(u))
+    nn_ = torch.sqrt(nx * nx + ny * ny)
+    pts = torch.stack((x, y, torch.zeros_like(x)), dim=2)
+    nrm = torch.stack((nx / nn_, ny / nn_, torch.zeros_like(x)), dim=2)
+    tgt = torch.cat((pts, nrm), dim=2).float()
+    c, sn = np.cos(0.03), np.sin(0.03)
+    Rz = torch.tensor([[c, -sn, 0.0], [sn, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    src = ((pts[:, :n] + 0.01 * torch.randn((N, n, 3), generator=gen, dtype=torch.float64) * torch.tensor([1.0, 1.0, 0.0], dtype=torch.float64)) @ Rz.T
+           + torch.tensor([0.1, -0.05, 0.0], dtype=torch.float64)).float()
+    if icp_type == "pt2pt":
+        tgt = tgt[:, :, :3].contiguous()
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1).requires_grad_(True)
+    icp = _icp(K, icp_type)
+    res = icp.icp(s, t, T0, trim_dist=TRIM, loss_fn=LOSS, dim=2)
+    wT = torch.arange(1, 13, dtype=torch.float32, device="cuda").reshape(3, 4)
+    (res["T"][:, :3, :] * wT).sum().backward()
+    cfg = IcpSettings(icp_type=icp_type, max_iterations=K, tolerance=1e-12, const_iter=True, trim_dist=TRIM,
+                      loss_name=LOSS["name"], loss_metric=LOSS["metric"], dim=2)
+    s64, t64 = src.double().requires_grad_(True), tgt.double().requires_grad_(True)
+    T64 = torch.eye(4, dtype=torch.float64).repeat(N, 1, 1).requires_grad_(True)
+    replay = [icp.last_correspondences[k].cpu().long() for k in range(K)]
+    ref = icp_forward(s64, t64, T64, torch.ones((N, n * (1 if icp_type == "pt2pl" else 3)), dtype=torch.float64), cfg, replay_idx=replay)
+    (ref["T"][:, :3, :] * wT.cpu().double()).sum().backward()
+    assert rel_err(res["T"].detach().cpu(), ref["T"].detach()) < 1e-5
+    assert rel_err(res["weights"].cpu(), ref["weights"]) < 1e-5
+    assert float(res["deltas"][:, :, [0, 1, 5], 0].abs().max()) == 0.0               # only (rot z, tx, ty) move
+    assert rel_err(s.grad.cpu(), s64.grad) < 1e-4 and rel_err(t.grad.cpu(), t64.grad) < 1e-4 and rel_err(T0.grad.cpu(), T64.grad) < 1e-4
+
+
+def test_early_stop_with_frozen_pairs_fp32_staged_equals_fp64_generic():
+    """Pairs of one batch converge at different iterations (ICP.py:240-260): frozen pairs get zero prior weight, the loop
+    ends when all are below the tolerance, stats are recorded at the first crossing.  The fp32 staged kernels must take
+    the same decisions as the fp64 generic path on the same problem (the tolerance sits between two well separated steps)."""
+    from dICP.ICP import ICP
+    from oracle.dicp_oracle import make_wavy_pair
+    N, n = 6, 2048
+    src, tgt = make_wavy_pair(N, n, 2500, seed=77, dtype=torch.float64, noise=0.0, extent=10.0)
+    c, sn = np.cos(0.12), np.sin(0.12)
+    Rz = torch.tensor([[c, -sn, 0.0], [sn, c, 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    src[3:] = src[3:] @ Rz.T + torch.tensor([0.9, 0.6, 0.1], dtype=torch.float64)     # the second half starts much further away
+    out = {}
+    for dt in (torch.float32, torch.float64):
+        icp = ICP(icp_type="pt2pl", differentiable=True, max_iterations=30, tolerance=2e-4)
+        s = src.to(dt).cuda().requires_grad_(True)
+        res = icp.icp(s, tgt.to(dt).cuda(), torch.eye(4, dtype=dt, device="cuda").repeat(N, 1, 1), trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        res["T"].sum().backward()
+        out[dt] = (res, s.grad)
+    r32, r64 = out[torch.float32][0], out[torch.float64][0]
+    assert r32["deltas"].shape == r64["deltas"].shape and r32["deltas"].shape[1] < 30
+    assert torch.equal(r32["stats"]["iterations"].cpu().double(), r64["stats"]["iterations"].cpu())
+    assert len(set(r64["stats"]["iterations"].cpu().tolist())) > 1, "the pairs were meant to stop at different iterations"
+    assert torch.equal(r32["stats"]["converged"].cpu(), r64["stats"]["converged"].cpu())
+    assert torch.allclose(r32["stats"]["matched_ratio"].cpu().double(), r64["stats"]["matched_ratio"].cpu(), atol=2e-3)
+    assert rel_err(r32["T"].detach().cpu(), r64["T"].detach().cpu()) < 2e-5
+    assert rel_err(r32["weights"].cpu(), r64["weights"].cpu()) < 1e-3
+    assert rel_err(out[torch.float32][1].cpu(), out[torch.float64][1].cpu()) < 5e-3
