@@ -320,3 +320,45 @@ def test_early_stop_with_frozen_pairs_fp32_staged_equals_fp64_generic():
     assert rel_err(r32["T"].detach().cpu(), r64["T"].detach().cpu()) < 2e-5
     assert rel_err(r32["weights"].cpu(), r64["weights"].cpu()) < 1e-3
     assert rel_err(out[torch.float32][1].cpu(), out[torch.float64][1].cpu()) < 5e-3
+
+
+@pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
+@pytest.mark.parametrize("diff,loss_name,metric,trim", [(False, "huber", 0.05, 1.0), (False, "cauchy", 0.3, None), (True, None, 1.0, None),
+                                                        (True, "huber", 0.1, None), (False, None, 1.0, 0.5)])
+def test_every_weight_option_through_the_staged_fp32_kernels(icp_type, diff, loss_name, metric, trim):
+    """The instantiations of the staged kernels that resolve the weight options at run time (everything but soft trim +
+    Cauchy / pseudo-Huber): hard trim, hard Huber, no loss, no trim (loss.py:21-58, ICP.py:152-169), fp32, forward and
+    backward against the fp64 oracle on the replayed correspondences."""
+    from dICP.ICP import ICP
+    from oracle.dicp_oracle import IcpSettings, icp_forward, make_wavy_pair
+    N, n, m, K = 3, 1536, 2000, 4
+    src, tgt = make_wavy_pair(N, n, m, seed=640, dtype=torch.float32, with_normals=icp_type == "pt2pl", extent=8.0)
+    gen = torch.Generator().manual_seed(5)
+    w = (0.5 + 0.5 * torch.rand((N, n), generator=gen)).cuda().requires_grad_(True)
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1).requires_grad_(True)
+    icp = ICP(icp_type=icp_type, differentiable=diff, max_iterations=K, tolerance=1e-12)
+    icp.const_iter = True
+    icp.keep_correspondences = True
+    loss_fn = {"name": loss_name, "metric": metric} if loss_name else None
+    res = icp.icp(s, t, T0, weight=w, trim_dist=trim, loss_fn=loss_fn, dim=3)
+    wT = torch.arange(1, 13, dtype=torch.float32, device="cuda").reshape(3, 4)
+    (res["T"][:, :3, :] * wT).sum().backward()
+    cfg = IcpSettings(icp_type=icp_type, max_iterations=K, tolerance=1e-12, const_iter=True, differentiable=diff, trim_dist=trim,
+                      loss_name=loss_name, loss_metric=metric, dim=3)
+    s64, t64 = src.double().requires_grad_(True), tgt.double().requires_grad_(True)
+    T64 = torch.eye(4, dtype=torch.float64).repeat(N, 1, 1).requires_grad_(True)
+    w64 = w.detach().cpu().double().requires_grad_(True)
+    replay = [icp.last_correspondences[k].cpu().long() for k in range(K)]
+    ref = icp_forward(s64, t64, T64, w64 if icp_type == "pt2pl" else w64.repeat_interleave(3, dim=1), cfg, replay_idx=replay)
+    (ref["T"][:, :3, :] * wT.cpu().double()).sum().backward()
+    assert rel_err(res["T"].detach().cpu(), ref["T"].detach()) < 1e-5
+    # hard thresholds (trim, Huber corner) may flip for a residual within fp32 rounding of the threshold: a handful of weights
+    wdiff = (res["weights"].cpu().double() - ref["weights"]).abs()
+    assert float((wdiff > 1e-4).double().mean()) < 1e-3
+    tol = 1e-4 if diff else 5e-3
+    assert rel_err(s.grad.cpu(), torch.nan_to_num(s64.grad)) < tol
+    assert rel_err(t.grad.cpu(), torch.nan_to_num(t64.grad)) < tol
+    assert rel_err(T0.grad.cpu(), torch.nan_to_num(T64.grad)) < tol
+    assert rel_err(w.grad.cpu(), torch.nan_to_num(w64.grad)) < tol
