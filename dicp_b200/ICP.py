@@ -97,6 +97,12 @@ class ICP:
         self.lazy_host_results = False
         self.use_svd = bool(func.get('svd', False))
         self.svd_literal = False
+        # not in the reference (optional YAML key dICP.functionality.sync_free): with const_iter set, icp() only
+        # enqueues its kernels and returns without waiting for the GPU -- the reference stops at every iteration
+        # (ICP.py:240) and torch.linalg.inv raises at once on a singular matrix (ICP.py:201).  A singular normal matrix
+        # then does not raise inside icp(); `check_status()` reports it for the most recent call.  Off by default.
+        self.sync_free = bool(func.get('sync_free', False))
+        self._last_status = None
 
     def icp(self, source, target, T_init, weight=None, trim_dist=None, loss_fn=None, dim=3):
         if self.use_svd and self.icp_type == 'pt2pt':
@@ -167,7 +173,7 @@ class ICP:
             self.icp_type, dim, self.diff, loss_name, loss_metric, trim_dist,
             self.config['dICP']['parameters']['tanh_steepness'], self.tolerance, self.max_iterations,
             self.const_iter, self.match_ratio_thresh, self.check_every,
-            self.nn_search if isinstance(self.nn_search, str) else 'brute')
+            self.nn_search if isinstance(self.nn_search, str) else 'brute', self.sync_free)
 
         if m_valid is not None and (len(m_valid) != N or min(m_valid) == target.shape[1]):
             m_valid = None                                   # nothing is padded
@@ -185,11 +191,13 @@ class ICP:
         # for the correspondences of every iteration
         nn_hook = None if isinstance(self.nn_search, str) else self.nn_search.bind(source_d.detach(), target_d.detach(), m_valid)
         keep = [] if self.keep_correspondences else None
+        status = []
         pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
             source_d, target_d, T_init.to(dev, non_blocking=True),
-            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook, keep, n_valid)
+            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook, keep, n_valid, status)
         if keep is not None:
             self.last_correspondences = keep[0]
+        self._last_status = status[0]
 
         if self.verbose:
             print("ICP converged in {} iterations".format(deltas.shape[1]))
@@ -212,6 +220,17 @@ class ICP:
             "weights": _Deferred(lambda: back(weights).unsqueeze(-1)),
             "stats": {"converged": back(converged), "iterations": back(num_iters), "matched_ratio": back(match_ratio)},
         })
+
+    def check_status(self):
+        """Not in the reference: waits for the most recent `icp()` call of this object and returns the number of
+        iterations it ran; raises the error a `sync_free` call could not raise at the time (a singular normal-equation
+        matrix, for which the reference's torch.linalg.inv raises at ICP.py:201)."""
+        if self._last_status is None:
+            return None
+        iters, singular = self._last_status.tolist()
+        if singular != 0.0:
+            raise RuntimeError("dicp_icp_forward: singular normal-equation matrix (torch.linalg.inv would raise, ICP.py:201)")
+        return int(iters)
 
     def _gumbel_loop(self, source, target, T_init, w_init, trim_dist, loss_fn, dim):
         """The Gauss-Newton loop (ICP.py:125-303) for `functionality.gumbel: True` with `differentiable=True`: every

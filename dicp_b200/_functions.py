@@ -213,7 +213,7 @@ class KabschICPFunction(torch.autograd.Function):
 
 
 def make_params(icp_type, dim, differentiable, loss_name, loss_metric, trim_dist, tanh_steepness, tolerance,
-                max_iterations, const_iter, match_ratio_thresh, check_every=1, nn_search="brute"):
+                max_iterations, const_iter, match_ratio_thresh, check_every=1, nn_search="brute", sync_free=False):
     if loss_name not in _lib.LOSS_IDS:
         raise ValueError("Invalid loss name: {}".format(loss_name))          # loss.py:19
     p = DicpParams()
@@ -229,6 +229,7 @@ def make_params(icp_type, dim, differentiable, loss_name, loss_metric, trim_dist
     if nn_search not in _lib.NN_MODES:
         raise ValueError("nn_search must be 'brute' or 'grid', got {!r}".format(nn_search))
     p.nn_mode = _lib.NN_MODES[nn_search]
+    p.flags = _lib.DICP_FLAG_NO_SYNC if (sync_free and const_iter) else 0
     p.loss_metric = float(loss_metric) if loss_name is not None else 1.0
     p.trim_dist = float(trim_dist) if use_trim else 0.0
     p.tanh_steepness = float(tanh_steepness)
@@ -251,7 +252,8 @@ class ICPFunction(torch.autograd.Function):
       (N, n) int32 tensor to fill, both views of this call's saved buffers, on the current stream."""
 
     @staticmethod
-    def forward(ctx, source, target, T_init, w_init, params, m_valid=None, nn_hook=None, keep_idx=None, n_valid=None):
+    def forward(ctx, source, target, T_init, w_init, params, m_valid=None, nn_hook=None, keep_idx=None, n_valid=None,
+                status_out=None):
         require_cuda()
         lib = load_library()
         dev, dt = source.device, source.dtype
@@ -314,6 +316,8 @@ class ICPFunction(torch.autograd.Function):
                               saved_idx, saved_state)
         if keep_idx is not None:                 # the caller asked for the correspondences (ICP.keep_correspondences)
             keep_idx.append(saved_idx[:k_run])
+        if status_out is not None:               # [iterations run, singular flag] of this call, still on the device
+            status_out.append(saved_state[0, 0, _lib.STATE_ITERS_RUN:_lib.STATE_SINGULAR + 1])
         outs = (pc, T, deltas[:, :k_run], weights[:, :k_run], costs[:, :k_run], converged.bool(), num_iters, match_ratio)
         ctx.mark_non_differentiable(*outs[2:])
         return outs
@@ -339,4 +343,4 @@ class ICPFunction(torch.autograd.Function):
                 ptr(saved_idx), ptr(saved_state), ptr(g_T), ptr(g_pc), ptr(g_src), ptr(g_tgt), ptr(g_w), ptr(g_T0),
                 ptr(ws), ws.numel(), stream_ptr(dev))
         check(rc, "dicp_icp_backward_" + sfx)
-        return g_src, g_tgt, g_T0, g_w, None, None, None, None, None
+        return g_src, g_tgt, g_T0, g_w, None, None, None, None, None, None

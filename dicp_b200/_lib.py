@@ -15,6 +15,8 @@ DICP_PT2PL, DICP_PT2PT = 0, 1
 LOSS_IDS = {None: 0, "huber": 1, "cauchy": 2}
 NN_MODES = {"brute": 0, "grid": 1}
 STATE_STRIDE = 64
+STATE_ITERS_RUN, STATE_SINGULAR = 62, 63      # DICP_STATE_ITERS_RUN / DICP_STATE_SINGULAR of record [0][0]
+DICP_FLAG_NO_SYNC = 1
 DICP_ERR_HOOK = -4          # a Python correspondence hook raised (dicp_icp_forward_hooked_*)
 
 
@@ -23,7 +25,7 @@ class DicpParams(ctypes.Structure):
     _fields_ = [
         ("icp_type", ctypes.c_int32), ("dim", ctypes.c_int32), ("differentiable", ctypes.c_int32),
         ("loss_id", ctypes.c_int32), ("use_trim", ctypes.c_int32), ("max_iterations", ctypes.c_int32),
-        ("const_iter", ctypes.c_int32), ("check_every", ctypes.c_int32), ("nn_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("const_iter", ctypes.c_int32), ("check_every", ctypes.c_int32), ("nn_mode", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("loss_metric", ctypes.c_double), ("trim_dist", ctypes.c_double), ("tanh_steepness", ctypes.c_double),
         ("tolerance", ctypes.c_double), ("match_ratio_thresh", ctypes.c_double),
     ]

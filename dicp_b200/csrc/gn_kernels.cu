@@ -649,7 +649,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 finalize_kernel(const T* __restrict__ source, int n, const double* __restrict__ state_all, int N, const Ctrl* __restrict__ ctrl,
                 double thresh, double rows, T* __restrict__ pc, T* __restrict__ T_out,
-                T* __restrict__ num_iters, T* __restrict__ match_ratio, const int32_t* __restrict__ n_valid) {
+                T* __restrict__ num_iters, T* __restrict__ match_ratio, const int32_t* __restrict__ n_valid,
+                double* status_rec) {
   const int b = blockIdx.y;
   const int nb = n_valid != nullptr ? min(n_valid[b], n) : n;      // padding rows of a ragged batch are zero points: pc = r
   const int kr = ctrl->iters_run;
@@ -668,6 +669,10 @@ finalize_kernel(const T* __restrict__ source, int n, const double* __restrict__ 
       rotate(C, p, a);
     }
     pc_b[3 * i] = a[0] + r[0]; pc_b[3 * i + 1] = a[1] + r[1]; pc_b[3 * i + 2] = a[2] + r[2];   // ICP.py:274
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && b == 0) {      // the call's status, for callers that did not wait for it
+    status_rec[DICP_STATE_ITERS_RUN] = (double)kr;
+    status_rec[DICP_STATE_SINGULAR] = ctrl->singular ? 1.0 : 0.0;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     T* To = T_out + (size_t)b * 16;                                                      // ICP.py:277-280
@@ -738,6 +743,8 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   const int nblk = gn_blocks_per_pair(N, n);
   const int check_every = p->check_every >= 1 ? p->check_every : 1;
   const size_t rec_stride = (size_t)N * ST_STRIDE;
+  // DICP_FLAG_NO_SYNC: a constant-iteration loop needs nothing from the device before it returns
+  const bool nosync = p->const_iter && (p->flags & DICP_FLAG_NO_SYNC);
 
   DICP_CUDA(cudaMemsetAsync(w.ctrl, 0, sizeof(Ctrl), st));
   init_state_kernel<T><<<(N + 127) / 128, 128, 0, st>>>(T_init, N, saved_state, converged, num_iters, match_ratio);
@@ -754,10 +761,12 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
     if (rc) return rc;
     rc = grid_sort_queries<T>(source, saved_state, N, n, gw, st);      // at the initial transform (record 0)
     if (rc) return rc;
-    int max_occ = 0;
-    DICP_CUDA(cudaMemcpyAsync(&max_occ, gw.max_occupancy, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DICP_CUDA(cudaStreamSynchronize(st));
-    if (max_occ > 64 && max_occ > m / 64) use_grid = false;
+    if (!nosync) {
+      int max_occ = 0;
+      DICP_CUDA(cudaMemcpyAsync(&max_occ, gw.max_occupancy, sizeof(int), cudaMemcpyDeviceToHost, st));
+      DICP_CUDA(cudaStreamSynchronize(st));
+      if (max_occ > 64 && max_occ > m / 64) use_grid = false;
+    }
   }
   if (!use_grid && hook == nullptr) {
     rc = nn_pack_targets<T>(target, N, m, S, m_valid, (V4*)w.packed, st);
@@ -793,8 +802,12 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
   }
   dim3 fgrid((n + 2047) / 2048 < 128 ? (n + 2047) / 2048 : 128, N);
   finalize_kernel<T><<<fgrid, 256, 0, st>>>(source, n, saved_state, N, w.ctrl, p->match_ratio_thresh, (double)nw,
-                                            pc, T_out, num_iters, match_ratio, n_valid);
+                                            pc, T_out, num_iters, match_ratio, n_valid, saved_state);
   DICP_LAUNCH_CHECK();
+  if (nosync) {                                   // the status stays in saved_state[0][0][DICP_STATE_ITERS_RUN / _SINGULAR]
+    *iters_run_host = K;
+    return 0;
+  }
   DICP_CUDA(cudaMemcpyAsync(&h, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   DICP_CUDA(cudaStreamSynchronize(st));
   *iters_run_host = h.iters_run;

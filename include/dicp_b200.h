@@ -33,7 +33,7 @@ extern "C" {
 #define DICP_API
 #endif
 
-#define DICP_VERSION 200
+#define DICP_VERSION 201
 
 #define DICP_ERR_ARG       -1   /* bad size / null pointer / unsupported option */
 #define DICP_ERR_WORKSPACE -2   /* workspace too small */
@@ -55,6 +55,18 @@ extern "C" {
 
 /* doubles per (iteration, pair) record in the saved-state buffer, see DESIGN.md §3 */
 #define DICP_STATE_STRIDE 64
+/* slots of record [0][pair 0] that receive the call's status when it ends: the number of iterations run and
+ * 1.0 if a normal-equation matrix was exactly singular (what a DICP_FLAG_NO_SYNC caller reads when it wants to) */
+#define DICP_STATE_ITERS_RUN 62
+#define DICP_STATE_SINGULAR  63
+
+/* dicp_params.flags.  DICP_FLAG_NO_SYNC: with const_iter set, dicp_icp_forward_* only ENQUEUES the loop and returns
+ * without synchronising the stream (the reference stops at every iteration, ICP.py:240, and torch.linalg.inv raises
+ * on a singular matrix, ICP.py:201): *iters_run_host = max_iterations, a singular matrix is not reported by the
+ * return value but left in saved_state[0][0][DICP_STATE_SINGULAR], and nn_mode GRID skips its host-side look at the
+ * cell occupancy (a badly clustered cloud is then searched through the grid's bounded fallback instead of the scan).
+ * Ignored when const_iter is 0. */
+#define DICP_FLAG_NO_SYNC 1
 
 /* Everything ICP.__init__ / ICP.dICP / config/dICP_config.yaml fix for one call. */
 typedef struct dicp_params {
@@ -68,7 +80,7 @@ typedef struct dicp_params {
   int32_t check_every;       /* host polls the device "all converged" flag every this
                                 many iterations when !const_iter (>=1; 1 == reference) */
   int32_t nn_mode;           /* DICP_NN_BRUTE | DICP_NN_GRID (not in the reference)         */
-  int32_t reserved;          /* keep the doubles 8-byte aligned                              */
+  int32_t flags;             /* DICP_FLAG_* bits, 0 == the reference's behaviour (not in the reference)     */
   double loss_metric;        /* loss_fn['metric']                    ICP.py:159  */
   double trim_dist;          /*                                      ICP.py:154  */
   double tanh_steepness;     /* yaml parameters.tanh_steepness       ICP.py:119  */
@@ -164,7 +176,8 @@ DICP_API int dicp_gather_rows_bwd_f64(const double* grad_out, const int32_t* idx
  * saved   saved_idx   [K,N,n] int32   correspondences of every iteration
  *         saved_state [(K+1),N,DICP_STATE_STRIDE] double  (C_k,r_k,active,delta_k,A_k ...)
  * iters_run_host: host int32, written before return (the call synchronises the stream
- *         once at its end, and every check_every iterations when !const_iter).          */
+ *         once at its end, and every check_every iterations when !const_iter; not at all with
+ *         const_iter and DICP_FLAG_NO_SYNC, see there).                                  */
 DICP_API size_t dicp_icp_workspace_bytes(int N, int n, int m, int elem_size);
 DICP_API int dicp_icp_forward_f32(const float* source, const float* target, const float* T_init, const float* w_init,
                          const int32_t* m_valid, const int32_t* n_valid, int N, int n, int m, int S, const dicp_params* params,

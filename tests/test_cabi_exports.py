@@ -30,7 +30,7 @@ def test_header_symbols_are_exported():
 
 def test_version_and_arg_errors():
     lib = _lib.load_library()
-    assert lib.dicp_version() == 200
+    assert lib.dicp_version() == 201
     assert lib.dicp_icp_workspace_bytes(256, 16384, 16384, 4) > 0
     assert lib.dicp_nn_workspace_bytes(1, 1, 1, 4) > 0
     # null pointers / bad sizes are rejected before any CUDA call

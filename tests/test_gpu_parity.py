@@ -916,3 +916,47 @@ def test_backward_matches_finite_differences(icp_type):
             fd = (vals[0] - vals[1]) / (2 * eps)
             an = float(leaf.grad.reshape(-1)[pidx])
             assert abs(fd - an) <= 2e-6 * max(1.0, abs(fd), abs(an)), (li, pidx, fd, an)
+
+
+@pytest.mark.parametrize("mode", ["brute", "grid"])
+def test_sync_free_call_equals_default_call(mode):
+    """`ICP.sync_free` (DICP_FLAG_NO_SYNC: a const_iter loop is only enqueued, no host synchronisation inside icp()):
+    bit-identical outputs and gradients, `check_status()` returns the iteration count afterwards; without const_iter
+    the flag is ignored."""
+    from oracle.dicp_oracle import make_wavy_pair
+    src, tgt = make_wavy_pair(3, 3000, 3500, seed=17, dtype=torch.float32)
+    T0 = torch.eye(4, device="cuda").repeat(3, 1, 1)
+    w = torch.rand(3, 3000, device="cuda") + 0.5
+    outs = {}
+    for sf in (False, True):
+        icp = _icp("pt2pl", True, 7, 1e-12, const_iter=True)
+        icp.nn_search, icp.sync_free = mode, sf
+        s, t = src.cuda().requires_grad_(True), tgt.cuda().requires_grad_(True)
+        wi = w.clone().requires_grad_(True)
+        res = icp.icp(s, t, T0, weight=wi, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+        (res["T"][:, :3, :] * torch.arange(1, 13, device="cuda").reshape(3, 4)).sum().backward()
+        assert icp.check_status() == 7
+        outs[sf] = (res["T"].detach(), res["pc"].detach(), res["weights"], res["deltas"], res["costs"], res["stats"]["iterations"],
+                    res["stats"]["matched_ratio"], s.grad.clone(), wi.grad.clone())
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a, b)
+    icp = _icp("pt2pl", True, 30, 1e-6, const_iter=False)
+    icp.sync_free = True
+    res = icp.icp(src.cuda(), tgt.cuda(), T0, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+    assert res["deltas"].shape[1] < 30 and icp.check_status() == res["deltas"].shape[1]
+
+
+def test_sync_free_reports_singular_system_afterwards():
+    """A NaN-poisoned cloud leaves no usable pivot: the default call raises inside icp() (as torch.linalg.inv does at
+    ICP.py:201); a sync_free call returns and `check_status()` raises the same error."""
+    from oracle.dicp_oracle import make_wavy_pair
+    src, tgt = make_wavy_pair(2, 1000, 1000, seed=3, dtype=torch.float32)
+    src[1, 5, 0] = float("nan")
+    T0 = torch.eye(4, device="cuda").repeat(2, 1, 1)
+    icp = _icp("pt2pl", True, 3, 1e-12, const_iter=True)
+    with pytest.raises(RuntimeError, match="singular"):
+        icp.icp(src.cuda(), tgt.cuda(), T0, dim=3)
+    icp.sync_free = True
+    icp.icp(src.cuda(), tgt.cuda(), T0, dim=3)
+    with pytest.raises(RuntimeError, match="singular"):
+        icp.check_status()
