@@ -439,6 +439,7 @@ def run_ours(args):
     T0_h = torch.eye(4).repeat(PAIRS_PER_GPU, 1, 1).pin_memory()
     icp = ICP(icp_type="pt2pl", differentiable=True, max_iterations=ITERS, tolerance=1e-12)
     icp.const_iter = True
+    icp.sync_free = True        # a constant-iteration loop is only enqueued: no host synchronisation inside icp()
     icp.device = dev
     theta = torch.arange(1, 13, dtype=torch.float32, device=dev).requires_grad_(True)
     model = WeightModel().to(dev)
@@ -624,6 +625,7 @@ def run_ours(args):
                             "loop consumes them; a caller who passes HOST tensors to icp() gets every result back on the host (plain dict, as upstream)"},
             "gpu_launches": launches_per_step * args.steps,
             "nn_search": "brute (tiled brute-force scan, the north-star kernel)",
+            "sync_free": True,
             "theta_only": {"value": pairs_total * steps_aux / sec_theta, "unit": "pairs/s", "ms_per_step": 1e3 * sec_theta / steps_aux,
                            "note": "round 1's step: weight=None, all-reduce of 13 floats"},
             "alt_nn_grid": {"value": pairs_total * steps_aux / sec_grid, "unit": "pairs/s", "ms_per_step": 1e3 * sec_grid / steps_aux,

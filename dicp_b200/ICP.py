@@ -47,6 +47,10 @@ class _Results(dict):
         return [self._force(k) for k in self.keys()]
 
 
+# pairs per kernel-side call (gridDim.y); larger batches are split by ICP.dICP
+_MAX_PAIRS_PER_CALL = 65535
+
+
 class _Deferred:
     def __init__(self, fn):
         self.fn = fn
@@ -192,12 +196,39 @@ class ICP:
         nn_hook = None if isinstance(self.nn_search, str) else self.nn_search.bind(source_d.detach(), target_d.detach(), m_valid)
         keep = [] if self.keep_correspondences else None
         status = []
-        pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
-            source_d, target_d, T_init.to(dev, non_blocking=True),
-            w_point.to(dev, non_blocking=True) if w_point is not None else None, params, m_valid, nn_hook, keep, n_valid, status)
+        T_init_d = T_init.to(dev, non_blocking=True)
+        w_d = w_point.to(dev, non_blocking=True) if w_point is not None else None
+        if N <= _MAX_PAIRS_PER_CALL or nn_hook is not None:
+            pc, T, deltas, weights, costs, converged, num_iters, match_ratio = _functions.ICPFunction.apply(
+                source_d, target_d, T_init_d, w_d, params, m_valid, nn_hook, keep, n_valid, status)
+        else:
+            # the kernels index pairs with gridDim.y: a larger batch runs as several calls.  Pairs are independent, so
+            # only the histories need care: the loop of the whole batch runs until its slowest pair has converged
+            # (ICP.py:239-257), and a part that stopped earlier is frozen from then on -- zero steps, weights and costs
+            # carried forward (ICP.py:224-232), which is what the padding below writes
+            parts = []
+            for lo in range(0, N, _MAX_PAIRS_PER_CALL):
+                sl = slice(lo, min(N, lo + _MAX_PAIRS_PER_CALL))
+                parts.append(_functions.ICPFunction.apply(
+                    source_d[sl], target_d[sl], T_init_d[sl], w_d[sl] if w_d is not None else None, params,
+                    m_valid[sl] if m_valid is not None else None, None, keep, n_valid[sl] if n_valid is not None else None, status))
+            K = max(p_[2].shape[1] for p_ in parts)
+
+            def hist(t, carry):
+                if t.shape[1] == K:
+                    return t
+                tail = t[:, -1:].expand(-1, K - t.shape[1], *t.shape[2:]) if carry else t.new_zeros((t.shape[0], K - t.shape[1]) + t.shape[2:])
+                return torch.cat((t, tail), dim=1)
+            pc, T = torch.cat([p_[0] for p_ in parts]), torch.cat([p_[1] for p_ in parts])
+            deltas = torch.cat([hist(p_[2], False) for p_ in parts])
+            weights = torch.cat([hist(p_[3], True) for p_ in parts])
+            costs = torch.cat([hist(p_[4], True) for p_ in parts])
+            converged, num_iters, match_ratio = (torch.cat([p_[i] for p_ in parts]) for i in (5, 6, 7))
+            if keep is not None:
+                keep[:] = [torch.cat([torch.cat((c, c[-1:].expand(K - c.shape[0], -1, -1))) for c in keep], dim=1)]
         if keep is not None:
             self.last_correspondences = keep[0]
-        self._last_status = status[0]
+        self._last_status = status
 
         if self.verbose:
             print("ICP converged in {} iterations".format(deltas.shape[1]))
@@ -225,12 +256,12 @@ class ICP:
         """Not in the reference: waits for the most recent `icp()` call of this object and returns the number of
         iterations it ran; raises the error a `sync_free` call could not raise at the time (a singular normal-equation
         matrix, for which the reference's torch.linalg.inv raises at ICP.py:201)."""
-        if self._last_status is None:
+        if not self._last_status:
             return None
-        iters, singular = self._last_status.tolist()
-        if singular != 0.0:
+        st = torch.stack(self._last_status).tolist()       # one [iterations run, singular flag] row per kernel-side call
+        if any(row[1] != 0.0 for row in st):
             raise RuntimeError("dicp_icp_forward: singular normal-equation matrix (torch.linalg.inv would raise, ICP.py:201)")
-        return int(iters)
+        return int(max(row[0] for row in st))
 
     def _gumbel_loop(self, source, target, T_init, w_init, trim_dist, loss_fn, dim):
         """The Gauss-Newton loop (ICP.py:125-303) for `functionality.gumbel: True` with `differentiable=True`: every

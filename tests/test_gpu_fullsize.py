@@ -210,6 +210,35 @@ def test_soft_trim_with_far_outliers_is_finite_and_matches_oracle():
     assert rel_err(t.grad.cpu(), t64.grad) < 1e-4
 
 
+def test_subnormal_distances_are_finite_and_match_oracle():
+    """Correspondences whose squared distance is a subnormal fp32 number (a cloud that touches the origin, registered
+    almost exactly): the branch-free fp32 square root must return ~0 for them (rsqrt flushes a subnormal argument to
+    zero and returns inf), as sqrtf does in the reference, not NaN."""
+    from oracle.dicp_oracle import make_wavy_pair
+    N, n, K = 2, 2048, 3
+    src, tgt = make_wavy_pair(N, n, n, seed=123, dtype=torch.float32)
+    tgt[:, :64, :3] = 0.0
+    tgt[:, :64, 2] = torch.arange(64, dtype=torch.float32) * 1e-3              # 64 targets on the z axis through the origin
+    src[:, :64] = tgt[:, :64, :3]
+    src[:, :64, 0] += torch.logspace(-24, -18, 64)                             # d^2 from 1e-48 (flushed) through the subnormal range to 1e-36
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1).requires_grad_(True)
+    w = torch.ones((N, n), device="cuda", requires_grad=True)
+    icp = _icp(K)
+    res = icp.icp(s, t, T0, weight=w, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+    wT = torch.arange(1, 13, dtype=torch.float32, device="cuda").reshape(3, 4)
+    wpc = torch.zeros((N, n, 3), device="cuda")
+    _loss(res, wT, wpc).backward()
+    for name, g in (("T", res["T"]), ("weights", res["weights"]), ("grad_source", s.grad), ("grad_target", t.grad), ("grad_w", w.grad)):
+        assert torch.isfinite(g).all(), name
+    ref, s64, t64, T64, w64 = oracle_replay(s, t, T0, w, icp.last_correspondences, [0, 1], K, wT, wpc)
+    assert rel_err(res["T"].detach().cpu(), ref["T"].detach()) < 1e-5
+    assert rel_err(res["weights"].cpu(), ref["weights"]) < 1e-5
+    assert rel_err(s.grad.cpu(), s64.grad) < 1e-4
+    assert rel_err(t.grad.cpu(), t64.grad) < 1e-4
+
+
 @pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
 @pytest.mark.parametrize("N,n", [(1, 4), (3, 8), (1, 12), (2, 252), (1, 256), (3, 260), (2, 508), (5, 512), (1, 516), (2, 1000),
                                  (7, 1028), (600, 64), (1, 2048), (2, 4100)])

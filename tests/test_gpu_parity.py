@@ -960,3 +960,38 @@ def test_sync_free_reports_singular_system_afterwards():
     icp.icp(src.cuda(), tgt.cuda(), T0, dim=3)
     with pytest.raises(RuntimeError, match="singular"):
         icp.check_status()
+
+
+def test_more_pairs_than_one_kernel_call_takes():
+    """N > 65535 pairs (gridDim.y): ICP.dICP splits the batch into several kernel-side calls.  Pairs are independent, so
+    every pair must come out exactly as in a small batch; with early stopping the histories of the part that converged
+    first are continued as the reference continues a frozen pair (zero steps, weights / costs carried forward)."""
+    torch.manual_seed(5)
+    N, n = 65535 + 150, 16
+    tgt = torch.rand(N, n, 3, dtype=torch.float64, device="cuda") * 4.0
+    ang = 0.05
+    R = torch.tensor([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64, device="cuda")
+    src = tgt @ R.T + 0.01
+    src[:65535] = tgt[:65535]                       # the first kernel-side call converges at once, the second needs a few iterations
+    T0 = torch.eye(4, dtype=torch.float64, device="cuda").repeat(N, 1, 1)
+    probe = [0, 7, 65534, 65535, 65600, N - 1]      # a small batch with pairs of both parts: the natural semantics
+    for const_iter in (True, False):
+        icp = _icp("pt2pt", True, 12, 1e-9, const_iter=const_iter)
+        icp.keep_correspondences = True
+        s = src.clone().requires_grad_(True)
+        res = icp.icp(s, tgt, T0, trim_dist=5.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+        res["T"][:, :3, :].sum().backward()
+        K = res["deltas"].shape[1]
+        assert res["T"].shape == (N, 4, 4) and res["pc"].shape == (N, n, 3) and res["weights"].shape == (N, K, 3 * n, 1)
+        assert icp.last_correspondences.shape == (K, N, n) and icp.check_status() == K
+        s2 = src[probe].clone().requires_grad_(True)
+        ref = icp.icp(s2, tgt[probe], T0[probe], trim_dist=5.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+        ref["T"][:, :3, :].sum().backward()
+        assert ref["deltas"].shape[1] == K
+        for key in ("T", "pc", "deltas", "weights", "costs"):
+            assert torch.equal(res[key][probe], ref[key]), key
+        for key in ("converged", "iterations", "matched_ratio"):
+            assert torch.equal(res["stats"][key][probe], ref["stats"][key]), key
+        assert torch.equal(s.grad[probe], s2.grad)
+        if not const_iter:
+            assert 2 < K < 12 and bool(res["stats"]["converged"].all())
