@@ -205,7 +205,7 @@ __device__ __forceinline__ void scatter_gtab(float* __restrict__ gtab, size_t ro
 // Ring stage = { idx | p | w0 | grad_source | grad_w } slices of the tile; see gn_accum_staged_kernel for the
 // full / empty barrier protocol, the rotating feeder and the state prefetch.
 // ---------------------------------------------------------------------------------------------------------
-template <bool PT2PL, bool FASTW>
+template <bool PT2PL, bool FASTW, bool RAGGED>
 __global__ void __launch_bounds__(BW_THREADS, BW_MINB)
 bwd_points_staged_kernel(const float* __restrict__ source, const void* __restrict__ rows, const float* __restrict__ w_init,
                          const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
@@ -239,9 +239,10 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
   typedef TileCursor Cursor;
   auto tile_count = [&](const Cursor& c) { return min(TILE, n - c.j * TILE); };
   // real correspondences of the tile: rows >= n_valid[b] of a ragged batch are padding, nothing flows into them
+  // (a compile-time option, as in gn_accum_staged_kernel)
   auto tile_valid = [&](const Cursor& c) {
-    const int nb = n_valid != nullptr ? min(n_valid[c.b], n) : n;
-    return max(0, min(TILE, nb - c.j * TILE));
+    if (!RAGGED) return min(TILE, n - c.j * TILE);
+    return max(0, min(TILE, min(n_valid[c.b], n) - c.j * TILE));
   };
   auto issue = [&](const Cursor& c) {
     const int s = c.L % STAGES;
@@ -540,18 +541,24 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
     const int32_t* idx_k = saved_idx + (size_t)k * N * n;
     if (staged) {
       if constexpr (sizeof(T) == 4) {
-#define DICP_BW_LAUNCH(PL, FW)                                                                                                     \
+#define DICP_BW_LAUNCH1(PL, FW, RG)                                                                                                \
   do {                                                                                                                             \
     if (smem > 48 * 1024)                                                                                                          \
-      DICP_CUDA(cudaFuncSetAttribute(bwd_points_staged_kernel<PL, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    bwd_points_staged_kernel<PL, FW><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
+      DICP_CUDA(cudaFuncSetAttribute(bwd_points_staged_kernel<PL, FW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    bwd_points_staged_kernel<PL, FW, RG><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
                                                                          grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w, w.bw_partials, nrows, plan, S, n_valid); \
+  } while (0)
+#define DICP_BW_LAUNCH(PL, FW)                         \
+  do {                                                 \
+    if (n_valid == nullptr) DICP_BW_LAUNCH1(PL, FW, false); \
+    else DICP_BW_LAUNCH1(PL, FW, true);                \
   } while (0)
         if (pl && fast) DICP_BW_LAUNCH(true, true);
         else if (pl) DICP_BW_LAUNCH(true, false);
         else if (fast) DICP_BW_LAUNCH(false, true);
         else DICP_BW_LAUNCH(false, false);
 #undef DICP_BW_LAUNCH
+#undef DICP_BW_LAUNCH1
       }
     } else {
 #define DICP_BW_LAUNCH(PL, FW)                                                                                                     \

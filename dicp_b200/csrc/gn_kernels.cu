@@ -148,7 +148,7 @@ __device__ __forceinline__ void gn_enter_segment(GnPairCtx<T>& ctx, int b, long 
 // requests per row (24-byte rows, cp.async into shared memory) measured slower -- the gather is bound by the request
 // rate through L1 / L2, not by registers or DRAM bytes.
 // ---------------------------------------------------------------------------------------------------------
-template <bool PT2PL, int DIM, bool FASTW>
+template <bool PT2PL, int DIM, bool FASTW, bool RAGGED>
 __global__ void __launch_bounds__(GN_THREADS, GN_MINB)
 gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict__ target, const void* __restrict__ rows,
                        const float* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, WeightParams P,
@@ -182,9 +182,10 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
   typedef TileCursor Cursor;
   auto tile_count = [&](const Cursor& c) { return min(TILE, n - c.j * TILE); };
   // correspondences of the tile that are real: rows >= n_valid[b] of a ragged batch are padding (never evaluated, weight 0)
+  // (RAGGED is a compile-time option: the per-tile look-up and the masks cost the dense kernel 3 %)
   auto tile_valid = [&](const Cursor& c) {
-    const int nb = n_valid != nullptr ? min(n_valid[c.b], n) : n;
-    return max(0, min(TILE, nb - c.j * TILE));
+    if (!RAGGED) return min(TILE, n - c.j * TILE);
+    return max(0, min(TILE, min(n_valid[c.b], n) - c.j * TILE));
   };
 
   // one lane feeds the ring
@@ -528,18 +529,20 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
   if (staged) {
     if constexpr (sizeof(T) == 4) {
       constexpr size_t smem = (size_t)GN_STAGES * GN_TILE * 20 + (GN_THREADS / 32) * (32 + 16) * sizeof(double) + 2 * GN_STAGES * sizeof(uint64_t);
-#define DICP_GN_LAUNCH1(PL, DM, FW)                                                                                                \
+#define DICP_GN_LAUNCH1(PL, DM, FW, RG)                                                                                             \
   do {                                                                                                                             \
     if (smem > 48 * 1024)             /* per device and cheap: no cached flag (a process may drive several devices) */             \
-      DICP_CUDA(cudaFuncSetAttribute(gn_accum_staged_kernel<PL, DM, FW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    gn_accum_staged_kernel<PL, DM, FW><<<dim3(plan.ctas, 1, 1), GN_THREADS, smem, st>>>(                                            \
+      DICP_CUDA(cudaFuncSetAttribute(gn_accum_staged_kernel<PL, DM, FW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gn_accum_staged_kernel<PL, DM, FW, RG><<<dim3(plan.ctas, 1, 1), GN_THREADS, smem, st>>>(                                        \
         source, target, (pl && rows24) ? nullptr : rows, w_init, idx, state, n, m, P, weights_out, w_pair_stride, partials, plan,  \
         stop_flag, N, n_valid);                                                                                                    \
   } while (0)
-#define DICP_GN_LAUNCH(PL, DM)             \
-  do {                                     \
-    if (fast) DICP_GN_LAUNCH1(PL, DM, true); \
-    else DICP_GN_LAUNCH1(PL, DM, false);   \
+#define DICP_GN_LAUNCH(PL, DM)                                  \
+  do {                                                          \
+    if (fast && n_valid == nullptr) DICP_GN_LAUNCH1(PL, DM, true, false); \
+    else if (fast) DICP_GN_LAUNCH1(PL, DM, true, true);         \
+    else if (n_valid == nullptr) DICP_GN_LAUNCH1(PL, DM, false, false); \
+    else DICP_GN_LAUNCH1(PL, DM, false, true);                  \
   } while (0)
       if (pl && p->dim == 3) DICP_GN_LAUNCH(true, 3);
       else if (pl) DICP_GN_LAUNCH(true, 2);

@@ -42,6 +42,10 @@ def child(pairs):
         sums = part.sum(dim=1)
         out[str(N)] = {"us": r["ms_per_launch"] * 1e3, "frac": r["frac"], "rows": part.shape[1],
                        "check": [float(sums[:, :31].abs().sum()), float(sums[N // 2, 0]), float(wout.double().sum())]}
+        if os.environ.get("SWEEP_BWD") and N <= 1024:      # one reverse iteration (pair kernel + point pass), with the weight gradient
+            rb = bench.roofline_bwd(src, tgt, pk, True)
+            out[str(N)]["bwd_us"] = rb["ms_per_launch"] * 1e3
+            out[str(N)]["bwd_frac"] = rb["frac"]
     print("RESULT " + json.dumps(out))
 
 
@@ -59,7 +63,9 @@ def main():
             print("%-12s FAILED\n%s" % (name, pr.stdout[-1500:]))
             continue
         d = json.loads(res[0][7:])
-        print("%-12s " % name + "  ".join("N=%s: %6.1f us %.3f rows=%d chk=%s" % (k, v["us"], v["frac"], v["rows"], ["%.9g" % c for c in v["check"]]) for k, v in d.items()), flush=True)
+        print("%-12s " % name + "  ".join("N=%s: %6.1f us %.3f rows=%d chk=%s%s" % (
+            k, v["us"], v["frac"], v["rows"], ["%.9g" % c for c in v["check"]],
+            " bwd %.1f us %.3f" % (v["bwd_us"], v["bwd_frac"]) if "bwd_us" in v else "") for k, v in d.items()), flush=True)
 
 
 if __name__ == "__main__":
