@@ -37,6 +37,11 @@ constexpr int BW_THREADS = 128;
 #ifndef BW_GTAB
 #define BW_GTAB 1          // 1: scatter into the aligned gradient table (two red.v4.f32), 0: into the caller's rows (three red.v2.f32)
 #endif
+#ifndef BW_PDL
+#define BW_PDL 2           // programmatic dependent launches in the reverse loop.  bit 1: the point pass starts while the pair kernel runs
+                           // (its prologue -- barriers, first streams, first row gathers -- needs nothing from it): 141.9 -> 137.4 us per
+                           // reverse iteration at C3.  bit 0: the pair kernel as a dependent of the point pass: 156 us (worse), off
+#endif
 constexpr int BW_TILE = BW_THREADS * BW_U;
 constexpr int BW_STAGE_BYTES = BW_TILE * 36;      // idx 4 + p 12 + w0 4 + grad_source 12 + grad_w 4 per correspondence
 
@@ -116,6 +121,11 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 bwd_pair_kernel(const double* __restrict__ partials, int nblk, int row_stride, const double* __restrict__ rec_k, int dim, int mode,
                 const T* __restrict__ grad_T, double* __restrict__ bw_state, T* __restrict__ grad_T_init, int N) {
+  // PDL: this kernel may have been launched while the point pass whose rows it sums was still running, and the next
+  // point pass may start its prologue (streams, first row gathers) while this kernel runs -- it waits before it reads
+  // bw_state.  The trigger comes after the wait, so whatever follows us also sees that point pass completed.
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= N) return;
@@ -128,8 +138,23 @@ bwd_pair_kernel(const double* __restrict__ partials, int nblk, int row_stride, c
     } else {
       mine = bw[lane];
     }
-    const double* rows_b = partials + (size_t)b * row_stride * BW_NRED + lane;
-    for (int j = 0; j < nblk; ++j) mine += rows_b[(size_t)j * BW_NRED];
+  }
+  {
+    // rows summed by two groups of 12 lanes (even / odd rows), four independent loads in flight per lane: fixed order
+    const int comp = lane % 12, grp = lane / 12;
+    double part = 0.0;
+    if (lane < 24) {
+      const double* rows_b = partials + (size_t)b * row_stride * BW_NRED + comp;
+      int j = grp;
+      for (; j + 6 < nblk; j += 8) {
+        const double a0 = rows_b[(size_t)j * BW_NRED], a1 = rows_b[(size_t)(j + 2) * BW_NRED], a2 = rows_b[(size_t)(j + 4) * BW_NRED],
+                     a3 = rows_b[(size_t)(j + 6) * BW_NRED];
+        part += a0; part += a1; part += a2; part += a3;
+      }
+      for (; j < nblk; j += 2) part += rows_b[(size_t)j * BW_NRED];
+    }
+    const double other = __shfl_down_sync(0xffffffffu, part, 12);
+    if (lane < 12) mine += part + other;
   }
   if (mode == 2) {
     if (lane < 12) {
@@ -369,14 +394,19 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
     }
   };
 
+  // PDL: everything up to here and the prologue below read only what kernels before the preceding bwd_pair_kernel
+  // wrote (saved correspondences, clouds, gather table, the running gradients of the previous point pass, which that
+  // pair kernel waited for before it let this grid start); the pair's (lambda, delta, carry) are read after pdl_wait()
+  pdl_trigger();
   if (tid == 0) issue(ci);
   ci.next(plan, walk);
-  prefetch_state(cg.b);
   Gathered ga, gb;
   gather(cg, ga);
   if (tid == 0) {
     for (int s = 1; s < STAGES - 1 && ci.L < ntiles; ++s) { issue(ci); ci.next(plan, walk); }
   }
+  pdl_wait();
+  prefetch_state(cg.b);
   {
     const int target_L = min(STAGES - 1, ntiles);
     Cursor t;
@@ -535,9 +565,14 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
     const double* rec_k = saved_state + (size_t)k * rec_stride;
     const bool first = k == iters_run - 1;
     // the first reverse step folds the seed pass's rows (one per seed CTA, contiguous), later ones the point pass's
-    bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, first ? nseed : nrows, first ? nseed : nrows, rec_k, p->dim, first ? 0 : 1,
-                                                    grad_T, w.bw_state, grad_T_init, N);
-    DICP_LAUNCH_CHECK();
+    if (first || !(BW_PDL & 1)) {
+      bwd_pair_kernel<T><<<pair_blocks, 128, 0, st>>>(w.bw_partials, first ? nseed : nrows, first ? nseed : nrows, rec_k, p->dim, first ? 0 : 1,
+                                                      grad_T, w.bw_state, grad_T_init, N);
+      DICP_LAUNCH_CHECK();
+    } else {     // scheduled while the point pass of iteration k + 1 drains (it waits for that grid's completion itself)
+      DICP_CUDA(launch_pdl(bwd_pair_kernel<T>, dim3(pair_blocks), dim3(128), 0, st, (const double*)w.bw_partials, nrows, nrows, rec_k, p->dim, 1,
+                           grad_T, w.bw_state, grad_T_init, N));
+    }
     const int32_t* idx_k = saved_idx + (size_t)k * N * n;
     if (staged) {
       if constexpr (sizeof(T) == 4) {
@@ -545,7 +580,12 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
   do {                                                                                                                             \
     if (smem > 48 * 1024)                                                                                                          \
       DICP_CUDA(cudaFuncSetAttribute(bwd_points_staged_kernel<PL, FW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    bwd_points_staged_kernel<PL, FW, RG><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
+    if (BW_PDL & 2) /* the prologue overlaps the pair kernel just launched */                                                      \
+      DICP_CUDA(launch_pdl(bwd_points_staged_kernel<PL, FW, RG>, dim3(plan.ctas), dim3(BW_THREADS), smem, st, source, (const void*)w.rows, w_init, \
+                           idx_k, rec_k, (const double*)w.bw_state, n, m, P, grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w,  \
+                           w.bw_partials, nrows, plan, S, n_valid));                                                               \
+    else                                                                                                                           \
+      bwd_points_staged_kernel<PL, FW, RG><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
                                                                          grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w, w.bw_partials, nrows, plan, S, n_valid); \
   } while (0)
 #define DICP_BW_LAUNCH(PL, FW)                         \
