@@ -488,14 +488,19 @@ def run_ours(args):
             slot["T0"].copy_(T0_h, non_blocking=True)
             slot["ready"].record(copy_stream)
 
+    # D2H: every step's result ([loss | dloss/dtheta] and T) goes to pinned host memory with an asynchronous copy; the host
+    # waits for it one step later (the loss it logs lags by a step, as in any pipelined training loop), so it never drains
+    # the launch queue -- with the grid search the step is short enough for that to cost 10 % otherwise
+    back = [{"vec": torch.empty(13, dtype=torch.float32).pin_memory(), "T": torch.empty((PAIRS_PER_GPU, 4, 4), dtype=torch.float32).pin_memory(),
+             "done": torch.cuda.Event()} for _ in range(2)]
+
     def e2e_loop(steps):
         cur = torch.cuda.current_stream(dev)
         for sl in slots:
             sl["free"].record(cur)
         enqueue_copy(slots[0])
-        out = None
         for i in range(steps):
-            sl = slots[i % 2]
+            sl, bk = slots[i % 2], back[i % 2]
             if i + 1 < steps:
                 enqueue_copy(slots[(i + 1) % 2])
             cur.wait_event(sl["ready"])
@@ -504,11 +509,16 @@ def run_ours(args):
             t = sl["tgt"].requires_grad_(True)
             loss, res = learning_step(s, t, sl["T0"])
             assert s.grad is not None and t.grad is not None
-            out = (torch.cat((loss.reshape(1), theta.grad)).cpu(), res["T"].detach().cpu())       # D2H: the step's result
+            bk["vec"].copy_(torch.cat((loss.reshape(1), theta.grad)), non_blocking=True)            # D2H: the step's result
+            bk["T"].copy_(res["T"].detach(), non_blocking=True)
+            bk["done"].record(cur)
             sl["src"].requires_grad_(False)
             sl["tgt"].requires_grad_(False)
             sl["free"].record(cur)
-        return out
+            if i > 0:
+                back[(i - 1) % 2]["done"].synchronize()                                             # the previous step's result is on the host
+        back[(steps - 1) % 2]["done"].synchronize()
+        return back[(steps - 1) % 2]["vec"].clone(), back[(steps - 1) % 2]["T"].clone()
 
     def timed(fn, steps, warmup, sampler=None, loop=False):
         if loop:
@@ -620,7 +630,8 @@ def run_ours(args):
             "e2e": {"value": pairs_total * steps_e2e / sec_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * sec_e2e / steps_e2e,
                     "api": "pinned host clouds -> H2D (double-buffered on a side stream) -> WeightModel -> dICP.ICP.ICP.icp -> backward to the "
-                           "model, the input points and T_init -> all-reduce -> D2H of [loss, dloss/dtheta] and T",
+                           "model, the input points and T_init -> all-reduce -> D2H of [loss, dloss/dtheta] and T into pinned host memory "
+                           "(asynchronous, awaited one step later)",
                     "note": "the gradients of the clouds (151 MB) and of the weight model stay on the GPU, where the optimiser of a training "
                             "loop consumes them; a caller who passes HOST tensors to icp() gets every result back on the host (plain dict, as upstream)"},
             "gpu_launches": launches_per_step * args.steps,
