@@ -51,6 +51,24 @@ with torch.no_grad():
     ms = timed(lambda: icp.icp(src, tgt, T0, dim=3))
 out["config2_pt2pt_64x4096_fwd"] = {"ms": ms, "pairs_per_s": 64 / ms * 1e3}
 
+# the same clouds through the Kabsch / SVD loop (functionality.svd, ICP.py:533-591): 10 iterations, forward and forward + backward
+icp_svd = ICP(icp_type="pt2pt", max_iterations=10, tolerance=0.0)
+icp_svd.use_svd = True
+icp_svd.check_every = 10
+with torch.no_grad():
+    ms = timed(lambda: icp_svd.icp(src, tgt, T0))
+out["config2_shape_kabsch_svd_64x4096_fwd"] = {"ms": ms, "pairs_per_s": 64 / ms * 1e3}
+src_g = src.clone().requires_grad_(True)
+
+
+def step_svd():
+    src_g.grad = None
+    icp_svd.icp(src_g, tgt, T0)["T"].sum().backward()
+
+
+ms = timed(step_svd)
+out["config2_shape_kabsch_svd_64x4096_fwd_bwd"] = {"ms": ms, "pairs_per_s": 64 / ms * 1e3}
+
 src, tgt = make_wavy_pair(1, 130000, 130000, seed=4000, dtype=torch.float32, extent=60.0)
 src, tgt, T0 = src.cuda().requires_grad_(True), tgt.cuda().requires_grad_(True), torch.eye(4, device="cuda").unsqueeze(0)
 icp = ICP(icp_type="pt2pl", max_iterations=10, tolerance=1e-12)
