@@ -274,6 +274,39 @@ def test_tile_ring_edge_shapes_vs_oracle(N, n, icp_type):
 
 
 @pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
+@pytest.mark.parametrize("K,n", [(1, 512), (2, 512), (1, 1001), (3, 1001), (2, 67), (3, 2050)])
+def test_short_loops_and_unaligned_clouds_vs_oracle(K, n, icp_type):
+    """One- and two-iteration loops (the reverse loop then consists of its first / last special steps only, with a single
+    programmatic dependent launch or none in between) and fp32 clouds whose length is not a multiple of 4 (they take the
+    generic fp32 accumulate / reverse kernels instead of the staged ones), forward and backward against the fp64 oracle
+    on the replayed correspondences."""
+    from oracle.dicp_oracle import make_wavy_pair
+    N = 3
+    m = n + 37
+    src, tgt = make_wavy_pair(N, n, m, seed=900 + n + K, dtype=torch.float32, with_normals=icp_type == "pt2pl", extent=6.0)
+    gen = torch.Generator().manual_seed(n + K)
+    w = (0.5 + 0.5 * torch.rand((N, n), generator=gen)).cuda().requires_grad_(True)
+    s = src.cuda().requires_grad_(True)
+    t = tgt.cuda().requires_grad_(True)
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1).requires_grad_(True)
+    icp = _icp(K, icp_type)
+    res = icp.icp(s, t, T0, weight=w, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+    assert res["deltas"].shape[1] == K
+    wT = torch.arange(1, 13, dtype=torch.float32, device="cuda").reshape(3, 4)
+    wpc = (0.01 * torch.linspace(-1.0, 1.0, n * 3, device="cuda").reshape(n, 3)).expand(N, n, 3).contiguous()
+    _loss(res, wT, wpc).backward()
+    pairs = [0, 1, 2]
+    ref, s64, t64, T64, w64 = oracle_replay(s, t, T0, w, icp.last_correspondences, pairs, K, wT, wpc, icp_type=icp_type)
+    assert rel_err(res["T"].detach().cpu(), ref["T"].detach()) < 2e-5
+    assert rel_err(res["pc"].detach().cpu(), ref["pc"].detach()) < 2e-5
+    assert rel_err(res["weights"].cpu(), ref["weights"]) < 2e-5
+    assert rel_err(s.grad.cpu(), s64.grad) < 5e-4
+    assert rel_err(t.grad.cpu(), t64.grad) < 5e-4
+    assert rel_err(w.grad.cpu(), w64.grad) < 5e-4
+    assert rel_err(T0.grad.cpu(), T64.grad) < 5e-4
+
+
+@pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
 def test_planar_problem_through_the_staged_fp32_kernels(icp_type):
     """dim = 2 (ICP.py:107-116, 186-189, 204-207) with n % 4 == 0 in fp32: the DIM = 2 instantiations of the staged
     accumulate / reverse kernels (the reference's own planar fixture has 65 points and takes the generic path)."""
