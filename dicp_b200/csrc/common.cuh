@@ -186,7 +186,8 @@ template <typename T> int grid_build(const T* tgt, int N, int m, int S, const in
 template <typename T> int grid_sort_queries(const T* q, const double* state, int N, int n, const GridWorkspace& g, cudaStream_t st);
 template <typename T>
 int grid_search(const T* q, const double* state, int N, int n, int m, const GridWorkspace& g, bool sorted, int32_t* idx_out, T* d2_out,
-                const int* stop_flag, cudaStream_t st);
+                const int* stop_flag, cudaStream_t st, const T* tgt = nullptr, int S = 3, const int32_t* warm_idx = nullptr);
+// warm_idx [N,n] (with tgt [N,m,S]): a neighbour candidate per query, e.g. the previous iteration's, that bounds the search
 
 // ---- Gauss-Newton (gn_kernels.cu) -----------------------------------------------------
 int gn_blocks_per_pair(int N, int n);   // partial-sum rows per pair of the accumulate kernel's tile plan (tile_stream.cuh)
