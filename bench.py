@@ -559,6 +559,18 @@ def run_ours(args):
     icp.nn_search = "grid"
     sec_grid, _ = timed(step_resident, steps_aux, 1)
     sec_grid_e2e, _ = timed(e2e_loop, steps_aux, 1, loop=True)
+    # the theta-only grid step (ICP forward + loss + backward, no weight model, no collective) eager and as ONE CUDA-graph
+    # replay per step (dicp_b200.graphs.GraphedStep: a sync-free call contains nothing that cannot be stream-captured)
+    from dicp_b200.graphs import GraphedStep
+
+    def grid_theta_step(s, t, T0):
+        res = icp.icp(s, t, T0, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        return torch.autograd.grad(learning_loss(res, theta.detach()), [s, t]) + (res["T"],)
+
+    sec_grid_theta, _ = timed(lambda: grid_theta_step(src_d, tgt_d, T0_d), steps_aux, 1)
+    graphed = GraphedStep(grid_theta_step, (src_d, tgt_d, T0_d))
+    sec_grid_graph, _ = timed(graphed.replay, steps_aux, 1)
+    del graphed
     icp.nn_search = "brute"
 
     # the collective alone: [loss | flat gradients] SUM all-reduce, as the step issues it
@@ -641,6 +653,8 @@ def run_ours(args):
                            "note": "round 1's step: weight=None, all-reduce of 13 floats"},
             "alt_nn_grid": {"value": pairs_total * steps_aux / sec_grid, "unit": "pairs/s", "ms_per_step": 1e3 * sec_grid / steps_aux,
                             "e2e": pairs_total * steps_aux / sec_grid_e2e,
+                            "theta_only": pairs_total * steps_aux / sec_grid_theta,
+                            "theta_only_cuda_graph_replay": pairs_total * steps_aux / sec_grid_graph,
                             "note": "same workload with ICP.nn_search='grid': exact uniform-grid NN built once per call, "
                                     "bit-identical correspondences (tests/test_gpu_parity.py::test_icp_grid_mode_equals_brute_mode)"},
             "roofline": roof, "roofline_gn": roof_gn, "roofline_bwd": roof_bwd, "cpu_baseline": cpu, "c4_split": c4,

@@ -1038,3 +1038,34 @@ def test_sync_free_step_can_be_captured_in_a_cuda_graph(mode):
     assert torch.equal(replayed[2], eager[2])                       # source gradient: plain read-modify-write, deterministic
     assert rel_err(replayed[3].cpu(), eager[3].cpu()) < 1e-5        # target gradient: atomics, order-dependent in the last bit
     assert not torch.equal(replayed[0], torch.eye(4, device="cuda").repeat(N, 1, 1))
+
+
+def test_graphed_step_helper_replays_a_whole_step_on_new_data():
+    """dicp_b200.graphs.GraphedStep: capture once, call with new clouds, get the eager results (forward outputs and the
+    gradient computed inside the step)."""
+    from dicp_b200.graphs import GraphedStep
+    from oracle.dicp_oracle import make_wavy_pair
+    N, n, m, K = 2, 2048, 2300, 5
+    icp = _icp("pt2pl", True, K, 1e-12, const_iter=True)
+    icp.nn_search, icp.sync_free = "grid", True
+    wT = torch.arange(1, 13, device="cuda", dtype=torch.float32).reshape(3, 4)
+
+    def step(source, target, T_init):
+        res = icp.icp(source, target, T_init, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+        g_src, = torch.autograd.grad((res["T"][:, :3, :] * wT).sum(), [source])
+        return {"T": res["T"], "pc": res["pc"], "g_src": g_src}
+
+    src, tgt = make_wavy_pair(N, n, m, seed=61, dtype=torch.float32)
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1)
+    graphed = GraphedStep(step, (src.cuda().requires_grad_(True), tgt.cuda(), T0))
+    for seed in (62, 63):
+        s2, t2 = make_wavy_pair(N, n, m, seed=seed, dtype=torch.float32)
+        T1 = T0.clone()
+        T1[:, 0, 3] = 0.01 * seed
+        out = graphed(s2.cuda(), t2.cuda(), T1)
+        got = {k: v.clone() for k, v in out.items()}
+        ref = step(s2.cuda().requires_grad_(True), t2.cuda(), T1)
+        for k in ("T", "pc", "g_src"):
+            assert torch.equal(got[k], ref[k]), k
+    with pytest.raises(ValueError):
+        graphed(src.cuda()[:, :100], tgt.cuda(), T0)
