@@ -793,7 +793,7 @@ static int icp_forward_impl(const T* source, const T* target, const T* T_init, c
     if (hook != nullptr) {
       rc = hook(hook_user, k, rec_k, idx_k);     // the caller's search (e.g. targets split over GPUs), stream-ordered
       if (rc) { set_error("dicp_icp_forward: the correspondence hook failed at iteration %d (code %d)", k, rc); return rc; }
-    } else if (use_grid) {      // from the second iteration on the previous neighbours bound the search (same result)
+    } else if (use_grid) {      // GRID_WARM (off): from the second iteration on the previous neighbours would bound the search
       rc = grid_search<T>(source, rec_k, N, n, m, gw, true, idx_k, nullptr, &w.ctrl->stop, st, target, S,
                           (GRID_WARM && k > 0) ? idx_k - (size_t)N * n : nullptr);
     }
