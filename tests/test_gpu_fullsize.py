@@ -424,3 +424,21 @@ def test_every_weight_option_through_the_staged_fp32_kernels(icp_type, diff, los
     assert rel_err(t.grad.cpu(), torch.nan_to_num(t64.grad)) < tol
     assert rel_err(T0.grad.cpu(), torch.nan_to_num(T64.grad)) < tol
     assert rel_err(w.grad.cpu(), torch.nan_to_num(w64.grad)) < tol
+
+
+def test_grid_mode_equals_brute_mode_at_benchmark_size():
+    """The solver with nn_search='grid' (uniform grid, row pruning by the best distance so far) against nn_search='brute'
+    on benchmark-sized clouds (4 pairs of 16 384 x 16 384 points, the bench generator): the same correspondences in
+    every iteration, hence bit-identical transforms and weights."""
+    from dicp_b200.synthetic import surface_pairs
+    N, n, K = 4, 16384, 5
+    src, tgt = surface_pairs(N, n, n, seed=3100, dtype=torch.float32, with_normals=True)
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1)
+    outs = {}
+    for mode in ("brute", "grid"):
+        icp = _icp(K)
+        icp.nn_search = mode
+        res = icp.icp(src.cuda(), tgt.cuda(), T0, trim_dist=TRIM, loss_fn=LOSS, dim=3)
+        outs[mode] = (icp.last_correspondences.clone(), res["T"].clone(), res["weights"].clone())
+    assert torch.equal(outs["brute"][0], outs["grid"][0])
+    assert torch.equal(outs["brute"][1], outs["grid"][1]) and torch.equal(outs["brute"][2], outs["grid"][2])
