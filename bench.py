@@ -371,9 +371,12 @@ def roofline_gn(src, tgt, idx, pk):
     sec = time_kernel(launch, reps=20)
     nbytes = 48.0 * N * n                    # p 12 + gathered (q,n) 24 + idx 4 + w_init 4 + weights write 4
     ach = nbytes / sec / 1e9
+    traffic = ncu_traffic("gn_accumulate", (N, n, m))
     return {"kernel": "gn_accum_staged_kernel<pt2pl,3> (one dicp_gn_accumulate_f32 call = the loop's single launch)", "bound": "hbm",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "traffic": ncu_traffic("gn_accumulate", (N, n, m)),
+            "traffic": traffic,
+            # the same launch by the bytes DRAM actually moved (ncu capture of this build; 32-byte gather records, 128-byte fills)
+            "frac_by_dram_traffic": traffic / sec / 1e9 / pk["hbm_gbs"] if traffic else None,
             "ms_per_launch": sec * 1e3, "peak_source": pk["source"], "bytes_per_correspondence": 48,
             "units_per_launch": float(N) * n, "pairs": N}
 
@@ -413,9 +416,10 @@ def roofline_bwd(src, tgt, pk, with_weight):
     # read p 12 + row 24 + idx 4 (+ w_init 4), RMW grad_source 24 (+ grad_w 8), atomic RMW grad_target 48
     nbytes = per * N * n
     ach = nbytes / sec / 1e9
+    traffic = ncu_traffic("bwd_points_124B" if with_weight else "bwd_points_112B", (N, n, m))
     return {"kernel": "bwd_points_staged_kernel<pt2pl> + bwd_pair_kernel, one reverse iteration", "bound": "hbm", "achieved": ach,
             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            "traffic": ncu_traffic("bwd_points_124B" if with_weight else "bwd_points_112B", (N, n, m)),
+            "traffic": traffic, "frac_by_dram_traffic": traffic / sec / 1e9 / pk["hbm_gbs"] if traffic else None,
             "ms_per_launch": sec * 1e3, "bytes_per_correspondence": per, "with_weight_gradient": with_weight, "units_per_launch": float(N) * n, "pairs": N,
             "whole_backward_ms": t10 * 1e3, "peak_source": pk["source"]}
 
@@ -601,7 +605,7 @@ def run_ours(args):
         # HBM fraction where launch ramp and tail do not dominate)
         big = 8
         big_src, big_tgt = src_d.detach().repeat(big, 1, 1), tgt_d.detach().repeat(big, 1, 1)
-        keep = ("achieved", "frac", "ms_per_launch", "units_per_launch")
+        keep = ("achieved", "frac", "ms_per_launch", "units_per_launch")      # (traffic fields exist for the C3 shape only)
         roof_gn["at_%d_pairs" % (big * PAIRS_PER_GPU)] = {k: v for k, v in roofline_gn(big_src, big_tgt, idx.repeat(big, 1), pk).items() if k in keep}
         del big_src, big_tgt
         roof_bwd = roofline_bwd(src_d.detach(), tgt_d.detach(), pk, True)
