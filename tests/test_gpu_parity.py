@@ -1069,3 +1069,27 @@ def test_graphed_step_helper_replays_a_whole_step_on_new_data():
             assert torch.equal(got[k], ref[k]), k
     with pytest.raises(ValueError):
         graphed(src.cuda()[:, :100], tgt.cuda(), T0)
+
+
+def test_sync_free_grid_on_a_badly_clustered_cloud_is_still_exact():
+    """The sync-free call skips the host-side look at the cell occupancy that makes the default call fall back to the
+    scan on badly clustered clouds; the grid search must then still return the scan's correspondences (a few far
+    outliers stretch the bounding box until almost every target shares a handful of cells; queries far from every
+    target take the bounded linear fallback)."""
+    torch.manual_seed(11)
+    N, n, m, K = 2, 1500, 2000, 4
+    tgt = torch.zeros(N, m, 6)
+    tgt[..., :3] = torch.randn(N, m, 3) * 0.05                       # a 10 cm blob
+    tgt[:, :5, :3] = torch.randn(N, 5, 3) * 400.0                    # five outliers hundreds of metres away
+    tgt[..., 3:] = torch.nn.functional.normalize(torch.randn(N, m, 3), dim=-1)
+    src = tgt[:, torch.randperm(m)[:n], :3] + 0.002 * torch.randn(N, n, 3)
+    src[:, :7] += 150.0                                              # and queries far from every target
+    T0 = torch.eye(4, device="cuda").repeat(N, 1, 1)
+    outs = {}
+    for mode, sf in (("brute", False), ("grid", True)):
+        icp = _icp("pt2pl", True, K, 1e-12, const_iter=True)
+        icp.nn_search, icp.sync_free, icp.keep_correspondences = mode, sf, True
+        res = icp.icp(src.cuda(), tgt.cuda(), T0, trim_dist=2.0, loss_fn={"name": "cauchy", "metric": 0.5}, dim=3)
+        outs[mode] = (icp.last_correspondences.clone(), res["T"].clone())
+        assert icp.check_status() == K
+    assert torch.equal(outs["brute"][0], outs["grid"][0]) and torch.equal(outs["brute"][1], outs["grid"][1])
