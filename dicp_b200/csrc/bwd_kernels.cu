@@ -230,7 +230,7 @@ __device__ __forceinline__ void scatter_gtab(float* __restrict__ gtab, size_t ro
 // Ring stage = { idx | p | w0 | grad_source | grad_w } slices of the tile; see gn_accum_staged_kernel for the
 // full / empty barrier protocol, the rotating feeder and the state prefetch.
 // ---------------------------------------------------------------------------------------------------------
-template <bool PT2PL, bool FASTW, bool RAGGED>
+template <bool PT2PL, bool FASTW, bool RAGGED, bool UNAL>
 __global__ void __launch_bounds__(BW_THREADS, BW_MINB)
 bwd_points_staged_kernel(const float* __restrict__ source, const void* __restrict__ rows, const float* __restrict__ w_init,
                          const int32_t* __restrict__ idx, const double* __restrict__ rec_k, const double* __restrict__ bw_state,
@@ -241,12 +241,18 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
   static_assert(STAGES >= 3, "a stage is refilled one step after its release");
   extern __shared__ __align__(128) unsigned char bw_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  auto st_idx = [&](int s) { return reinterpret_cast<int32_t*>(bw_smem + (size_t)s * BW_STAGE_BYTES); };
-  auto st_p = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 4); };
-  auto st_w = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 16); };
-  auto st_gs = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 20); };
-  auto st_gw = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * BW_STAGE_BYTES + TILE * 32); };
-  double* red_smem = reinterpret_cast<double*>(bw_smem + (size_t)STAGES * BW_STAGE_BYTES);
+  // UNAL: clouds whose length is not a multiple of 4 -- the feeder copies the aligned superset of a tile's slice of every
+  // stream and the consumers read at the slice's offset inside it (see gn_accum_staged_kernel)
+  constexpr int STG = TILE + (UNAL ? 8 : 0);
+  constexpr size_t STAGE_BYTES = (size_t)STG * 36;
+  auto st_idx = [&](int s) { return reinterpret_cast<int32_t*>(bw_smem + (size_t)s * STAGE_BYTES); };
+  auto st_p = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * STAGE_BYTES + STG * 4); };
+  auto st_w = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * STAGE_BYTES + STG * 16); };
+  auto st_gs = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * STAGE_BYTES + STG * 20); };
+  auto st_gw = [&](int s) { return reinterpret_cast<float*>(bw_smem + (size_t)s * STAGE_BYTES + STG * 32); };
+  auto st_off = [&](const TileCursor& c) { return UNAL ? ((c.b & 3) * (n & 3)) & 3 : 0; };      // (b n + j TILE) mod 4
+  const int idx_mis = UNAL ? (int)((reinterpret_cast<uintptr_t>(idx) >> 2) & 3) : 0;              // elements past a 16-byte boundary
+  double* red_smem = reinterpret_cast<double*>(bw_smem + (size_t)STAGES * STAGE_BYTES);
   double* slot = red_smem + WARPS * 32 + warp * 32;            // this warp's copy of the next segment's pair record
   uint64_t* full = reinterpret_cast<uint64_t*>(red_smem + WARPS * 32 + WARPS * 32);
   uint64_t* empty = full + STAGES;
@@ -273,6 +279,38 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
     const int s = c.L % STAGES;
     const uint32_t cnt = (uint32_t)tile_count(c);
     const size_t o = (size_t)c.b * n + c.j * TILE;
+    if (UNAL) {
+      // aligned supersets of the slices, tails behind the last whole 16-byte group by ordinary copies: see gn_accum_staged_kernel
+      const long long total = (long long)(plan.tiles / plan.tpp) * n, oo = (long long)o;
+      auto span = [&](int mis, long long& a0, uint32_t& nb) {
+        a0 = ((oo + mis) & ~3LL) - mis;
+        long long a1 = ((oo + cnt + mis + 3) & ~3LL) - mis;
+        const long long lim = ((total + mis) & ~3LL) - mis;
+        if (a1 > lim) a1 = lim;
+        nb = a1 > a0 ? (uint32_t)(a1 - a0) : 0u;
+      };
+      long long a0, ai0;
+      uint32_t nb, nbi;
+      span(0, a0, nb);
+      span(idx_mis, ai0, nbi);
+      for (long long e = (a0 + nb > oo ? a0 + nb : oo); e < oo + cnt; ++e) {
+        const long long k = e - a0;
+#pragma unroll
+        for (int c3 = 0; c3 < 3; ++c3) { st_p(s)[k * 3 + c3] = source[e * 3 + c3]; st_gs(s)[k * 3 + c3] = grad_source[e * 3 + c3]; }
+        if (w_init != nullptr) st_w(s)[k] = w_init[e];
+        if (grad_w != nullptr) st_gw(s)[k] = grad_w[e];
+      }
+      for (long long e = (ai0 + nbi > oo ? ai0 + nbi : oo); e < oo + cnt; ++e) st_idx(s)[e - ai0] = idx[e];
+      mbar_expect_tx(&full[s], nbi * 4u + nb * (24u + (w_init != nullptr ? 4u : 0u) + (grad_w != nullptr ? 4u : 0u)));
+      if (nbi > 0u) bulk_g2s(st_idx(s), idx + ai0, nbi * 4u, &full[s]);
+      if (nb > 0u) {
+        bulk_g2s(st_p(s), source + a0 * 3, nb * 12u, &full[s]);
+        bulk_g2s(st_gs(s), grad_source + a0 * 3, nb * 12u, &full[s]);
+        if (w_init != nullptr) bulk_g2s(st_w(s), w_init + a0, nb * 4u, &full[s]);
+        if (grad_w != nullptr) bulk_g2s(st_gw(s), grad_w + a0, nb * 4u, &full[s]);
+      }
+      return;
+    }
     mbar_expect_tx(&full[s], cnt * (28u + (w_init != nullptr ? 4u : 0u) + (grad_w != nullptr ? 4u : 0u)));
     bulk_g2s(st_idx(s), idx + o, cnt * 4u, &full[s]);
     bulk_g2s(st_p(s), source + o * 3, cnt * 12u, &full[s]);
@@ -298,7 +336,7 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
     const size_t row_b = (size_t)c.b * m;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = tid * U + u < cnt ? st_idx(s)[tid * U + u] : 0;
+      const int j = tid * U + u < cnt ? st_idx(s)[((st_off(c) + idx_mis) & 3) + tid * U + u] : 0;
       g.jj[u] = j;
       load_packed_row<float, PT2PL>(rows, row_b + j, g.q[u], g.nr[u]);
     }
@@ -338,12 +376,13 @@ bwd_points_staged_kernel(const float* __restrict__ source, const void* __restric
     const int cnt = tile_valid(cc);
     // this lane's staged inputs
     float p[U][3], gs[U][3], w0[U], gw[U];
+    const int off = st_off(cc);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { p[u][c] = st_p(s)[(tid * U + u) * 3 + c]; gs[u][c] = st_gs(s)[(tid * U + u) * 3 + c]; }
-      w0[u] = w_init != nullptr ? st_w(s)[tid * U + u] : 1.0f;
-      gw[u] = grad_w != nullptr ? st_gw(s)[tid * U + u] : 0.0f;
+      for (int c = 0; c < 3; ++c) { p[u][c] = st_p(s)[(off + tid * U + u) * 3 + c]; gs[u][c] = st_gs(s)[(off + tid * U + u) * 3 + c]; }
+      w0[u] = w_init != nullptr ? st_w(s)[off + tid * U + u] : 1.0f;
+      gw[u] = grad_w != nullptr ? st_gw(s)[off + tid * U + u] : 0.0f;
     }
     cg.next(plan, walk);
     if (cg.L < ntiles) {
@@ -546,8 +585,7 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   // fast path: the streams move as 16-byte aligned slices; the gather table is rebuilt here (the workspace of the
   // forward call may have been reused in between), the gradient table lives in the workspace
-  const bool staged = sizeof(T) == 4 && (n % 4) == 0 && aligned16(source) && aligned16(saved_idx) && aligned16(w_init) &&
-                      aligned16(grad_source) && aligned16(grad_w) && (((size_t)N * n) % 4) == 0;
+  const bool staged = sizeof(T) == 4 && aligned16(source) && aligned16(saved_idx) && aligned16(w_init) && aligned16(grad_source) && aligned16(grad_w);
 
   if (staged) {
     int rc = gn_pack_rows<T>(target, N, m, S, pl, w.rows, st);
@@ -560,7 +598,8 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
   if (grad_w != nullptr) DICP_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)N * n * sizeof(T), st));
   bwd_seed_kernel<T><<<dim3(nseed, N), BW_THREADS, 0, st>>>(source, grad_pc, saved_state + (size_t)iters_run * rec_stride, n, grad_source, w.bw_partials, n_valid);
   DICP_LAUNCH_CHECK();
-  constexpr size_t smem = (size_t)BW_STAGES * BW_STAGE_BYTES + (BW_THREADS / 32) * 64 * sizeof(double) + 2 * BW_STAGES * sizeof(uint64_t);
+  constexpr size_t smem_rest = (BW_THREADS / 32) * 64 * sizeof(double) + 2 * BW_STAGES * sizeof(uint64_t);
+  const bool unal = (n % 4) != 0;
   for (int k = iters_run - 1; k >= 0; --k) {
     const double* rec_k = saved_state + (size_t)k * rec_stride;
     const bool first = k == iters_run - 1;
@@ -576,17 +615,23 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
     const int32_t* idx_k = saved_idx + (size_t)k * N * n;
     if (staged) {
       if constexpr (sizeof(T) == 4) {
-#define DICP_BW_LAUNCH1(PL, FW, RG)                                                                                                \
+#define DICP_BW_LAUNCH2(PL, FW, RG, UA)                                                                                            \
   do {                                                                                                                             \
+    constexpr size_t smem = (size_t)BW_STAGES * (BW_TILE + ((UA) ? 8 : 0)) * 36 + smem_rest;                                       \
     if (smem > 48 * 1024)                                                                                                          \
-      DICP_CUDA(cudaFuncSetAttribute(bwd_points_staged_kernel<PL, FW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      DICP_CUDA(cudaFuncSetAttribute(bwd_points_staged_kernel<PL, FW, RG, UA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     if (BW_PDL & 2) /* the prologue overlaps the pair kernel just launched */                                                      \
-      DICP_CUDA(launch_pdl(bwd_points_staged_kernel<PL, FW, RG>, dim3(plan.ctas), dim3(BW_THREADS), smem, st, source, (const void*)w.rows, w_init, \
+      DICP_CUDA(launch_pdl(bwd_points_staged_kernel<PL, FW, RG, UA>, dim3(plan.ctas), dim3(BW_THREADS), smem, st, source, (const void*)w.rows, w_init, \
                            idx_k, rec_k, (const double*)w.bw_state, n, m, P, grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w,  \
                            w.bw_partials, nrows, plan, S, n_valid));                                                               \
     else                                                                                                                           \
-      bwd_points_staged_kernel<PL, FW, RG><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
+      bwd_points_staged_kernel<PL, FW, RG, UA><<<plan.ctas, BW_THREADS, smem, st>>>(source, w.rows, w_init, idx_k, rec_k, w.bw_state, n, m, P, \
                                                                          grad_source, BW_GTAB ? (float*)w.gtab : (float*)grad_target, grad_w, w.bw_partials, nrows, plan, S, n_valid); \
+  } while (0)
+#define DICP_BW_LAUNCH1(PL, FW, RG)              \
+  do {                                           \
+    if (unal) DICP_BW_LAUNCH2(PL, FW, RG, true); \
+    else DICP_BW_LAUNCH2(PL, FW, RG, false);     \
   } while (0)
 #define DICP_BW_LAUNCH(PL, FW)                         \
   do {                                                 \
@@ -599,6 +644,7 @@ static int icp_backward_impl(const T* source, const T* target, const T* w_init, 
         else DICP_BW_LAUNCH(false, false);
 #undef DICP_BW_LAUNCH
 #undef DICP_BW_LAUNCH1
+#undef DICP_BW_LAUNCH2
       }
     } else {
 #define DICP_BW_LAUNCH(PL, FW)                                                                                                     \

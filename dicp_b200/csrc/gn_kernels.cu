@@ -153,7 +153,7 @@ __device__ __forceinline__ void gn_enter_segment(GnPairCtx<T>& ctx, int b, long 
 // requests per row (24-byte rows, cp.async into shared memory) measured slower -- the gather is bound by the request
 // rate through L1 / L2, not by registers or DRAM bytes.
 // ---------------------------------------------------------------------------------------------------------
-template <bool PT2PL, int DIM, bool FASTW, bool RAGGED>
+template <bool PT2PL, int DIM, bool FASTW, bool RAGGED, bool UNAL>
 __global__ void __launch_bounds__(GN_THREADS, GN_MINB)
 gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict__ target, const void* __restrict__ rows,
                        const float* __restrict__ w_init, const int32_t* __restrict__ idx, StateView state, int n, int m, WeightParams P,
@@ -165,10 +165,16 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
   // dynamic shared memory: STAGES x { idx[TILE] | p[3 TILE] | w0[TILE] } (20 TILE bytes), reduction scratch, state slots, barriers
   extern __shared__ __align__(128) unsigned char gn_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  auto st_idx = [&](int s) { return reinterpret_cast<int32_t*>(gn_smem + (size_t)s * TILE * 20); };
-  auto st_p = [&](int s) { return reinterpret_cast<float*>(gn_smem + (size_t)s * TILE * 20 + TILE * 4); };
-  auto st_w = [&](int s) { return reinterpret_cast<float*>(gn_smem + (size_t)s * TILE * 20 + TILE * 16); };
-  double* red_smem = reinterpret_cast<double*>(gn_smem + (size_t)STAGES * TILE * 20);
+  // UNAL: the clouds' length is not a multiple of 4, so a tile's slice of the streams does not start on a 16-byte
+  // boundary.  The feeder then copies the aligned superset of the slice (up to three elements more at either end; a
+  // stage has room for TILE + 8) and the consumers read at the slice's offset inside it.
+  constexpr int STG = TILE + (UNAL ? 8 : 0);
+  auto st_idx = [&](int s) { return reinterpret_cast<int32_t*>(gn_smem + (size_t)s * STG * 20); };
+  auto st_p = [&](int s) { return reinterpret_cast<float*>(gn_smem + (size_t)s * STG * 20 + STG * 4); };
+  auto st_w = [&](int s) { return reinterpret_cast<float*>(gn_smem + (size_t)s * STG * 20 + STG * 16); };
+  auto st_off = [&](const TileCursor& c) { return UNAL ? ((c.b & 3) * (n & 3)) & 3 : 0; };      // (b n + j TILE) mod 4
+  const int idx_mis = UNAL ? (int)((reinterpret_cast<uintptr_t>(idx) >> 2) & 3) : 0;              // elements past a 16-byte boundary
+  double* red_smem = reinterpret_cast<double*>(gn_smem + (size_t)STAGES * STG * 20);
   double* slot = red_smem + WARPS * 32 + warp * 16;            // this warp's (C, r, active) record of the next segment
   uint64_t* full = reinterpret_cast<uint64_t*>(red_smem + WARPS * 32 + WARPS * 16);
   uint64_t* empty = full + STAGES;
@@ -199,6 +205,35 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
     const int i0 = c.j * TILE;
     const uint32_t cnt = (uint32_t)tile_count(c);
     const size_t o = (size_t)c.b * n + i0;
+    if (UNAL) {
+      // aligned superset [a0, a0 + nb) of the slice [o, o + cnt) of a stream whose base is `mis` elements past a 16-byte
+      // boundary; it never passes the last whole 16-byte group of the array (what is left of the slice behind it, at
+      // most three elements, is copied with ordinary loads and stores and released by the arrival below)
+      const long long total = (long long)N * n, oo = (long long)o;
+      auto span = [&](int mis, long long& a0, uint32_t& nb) {
+        a0 = ((oo + mis) & ~3LL) - mis;
+        long long a1 = ((oo + cnt + mis + 3) & ~3LL) - mis;
+        const long long lim = ((total + mis) & ~3LL) - mis;
+        if (a1 > lim) a1 = lim;
+        nb = a1 > a0 ? (uint32_t)(a1 - a0) : 0u;
+      };
+      long long a0, ai0;
+      uint32_t nb, nbi;
+      span(0, a0, nb);                 // source, w_init: 16-byte aligned bases
+      span(idx_mis, ai0, nbi);         // the indices of iteration k start k N n elements into the saved buffer
+      for (long long e = (a0 + nb > oo ? a0 + nb : oo); e < oo + cnt; ++e) {
+        st_p(s)[(e - a0) * 3] = source[e * 3]; st_p(s)[(e - a0) * 3 + 1] = source[e * 3 + 1]; st_p(s)[(e - a0) * 3 + 2] = source[e * 3 + 2];
+        if (w_init != nullptr) st_w(s)[e - a0] = w_init[e];
+      }
+      for (long long e = (ai0 + nbi > oo ? ai0 + nbi : oo); e < oo + cnt; ++e) st_idx(s)[e - ai0] = idx[e];
+      mbar_expect_tx(&full[s], nbi * 4u + nb * (w_init != nullptr ? 16u : 12u));
+      if (nbi > 0u) bulk_g2s(st_idx(s), idx + ai0, nbi * 4u, &full[s]);
+      if (nb > 0u) {
+        bulk_g2s(st_p(s), source + a0 * 3, nb * 12u, &full[s]);
+        if (w_init != nullptr) bulk_g2s(st_w(s), w_init + a0, nb * 4u, &full[s]);
+      }
+      return;
+    }
     mbar_expect_tx(&full[s], cnt * (w_init != nullptr ? 20u : 16u));
 #if GN_L2HINT
     const uint64_t pol_stream = l2_policy_evict_first();       // read-once streams must not push the gather table out of L2
@@ -252,12 +287,13 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
     const size_t row_b = (size_t)c.b * m;
     const bool last_pair = c.b == N - 1;                       // the very last row of the tensor must not be over-read
     int jj[U];
-    if (U == 4) {
+    const int off = st_off(c);
+    if (U == 4 && !UNAL) {
       const int4 v = *reinterpret_cast<const int4*>(st_idx(s) + tid * U);
       jj[0] = v.x; jj[1 % U] = v.y; jj[2 % U] = v.z; jj[3 % U] = v.w;
     } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) jj[u] = st_idx(s)[tid * U + u];
+      for (int u = 0; u < U; ++u) jj[u] = st_idx(s)[((off + idx_mis) & 3) + tid * U + u];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -275,26 +311,27 @@ gn_accum_staged_kernel(const float* __restrict__ source, const float* __restrict
   // this lane's points and prior weights of the tile, from the ring
   auto read_stage = [&](const Cursor& c, Staged& in) {
     const int s = c.L % STAGES;
+    const int off = st_off(c);
     const float4* sp = reinterpret_cast<const float4*>(st_p(s) + tid * U * 3);
     float flat[U * 3];
-    if (U == 4) {
+    if (U == 4 && !UNAL) {
       const float4 a = sp[0], bq = sp[1], cq = sp[2];
       flat[0] = a.x; flat[1] = a.y; flat[2] = a.z; flat[3] = a.w;
       flat[4 % (U * 3)] = bq.x; flat[5 % (U * 3)] = bq.y; flat[6 % (U * 3)] = bq.z; flat[7 % (U * 3)] = bq.w;
       flat[8 % (U * 3)] = cq.x; flat[9 % (U * 3)] = cq.y; flat[10 % (U * 3)] = cq.z; flat[11 % (U * 3)] = cq.w;
     } else {
 #pragma unroll
-      for (int k = 0; k < U * 3; ++k) flat[k] = st_p(s)[tid * U * 3 + k];
+      for (int k = 0; k < U * 3; ++k) flat[k] = st_p(s)[(off + tid * U) * 3 + k];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) { in.p[u][0] = flat[3 * u]; in.p[u][1] = flat[3 * u + 1]; in.p[u][2] = flat[3 * u + 2]; }
     if (w_init != nullptr) {
-      if (U == 4) {
+      if (U == 4 && !UNAL) {
         const float4 w4 = *reinterpret_cast<const float4*>(st_w(s) + tid * U);
         in.w0[0] = w4.x; in.w0[1 % U] = w4.y; in.w0[2 % U] = w4.z; in.w0[3 % U] = w4.w;
       } else {
 #pragma unroll
-        for (int u = 0; u < U; ++u) in.w0[u] = st_w(s)[tid * U + u];
+        for (int u = 0; u < U; ++u) in.w0[u] = st_w(s)[off + tid * U + u];
       }
     } else {
 #pragma unroll
@@ -530,17 +567,25 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   // the staged kernel moves 16-byte aligned slices of the streams with bulk copies
   const bool rows24 = GN_ROWS24 && pl && S == 6 && aligned16(target);      // see load_row24
-  const bool staged = sizeof(T) == 4 && (rows24 || rows != nullptr) && (n % 4) == 0 && aligned16(source) && aligned16(idx) && aligned16(w_init);
+  const bool unal = (n % 4) != 0;       // the staged kernel then copies aligned supersets of the slices (UNAL)
+  const bool staged = sizeof(T) == 4 && (rows24 || rows != nullptr) && aligned16(source) && aligned16(w_init) &&
+                      (unal ? !GN_ROWS24 : aligned16(idx));
   if (staged) {
     if constexpr (sizeof(T) == 4) {
-      constexpr size_t smem = (size_t)GN_STAGES * GN_TILE * 20 + (GN_THREADS / 32) * (32 + 16) * sizeof(double) + 2 * GN_STAGES * sizeof(uint64_t);
-#define DICP_GN_LAUNCH1(PL, DM, FW, RG)                                                                                             \
+      constexpr size_t smem_rest = (GN_THREADS / 32) * (32 + 16) * sizeof(double) + 2 * GN_STAGES * sizeof(uint64_t);
+#define DICP_GN_LAUNCH2(PL, DM, FW, RG, UA)                                                                                         \
   do {                                                                                                                             \
+    constexpr size_t smem = (size_t)GN_STAGES * (GN_TILE + ((UA) ? 8 : 0)) * 20 + smem_rest;                                       \
     if (smem > 48 * 1024)             /* per device and cheap: no cached flag (a process may drive several devices) */             \
-      DICP_CUDA(cudaFuncSetAttribute(gn_accum_staged_kernel<PL, DM, FW, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    gn_accum_staged_kernel<PL, DM, FW, RG><<<dim3(plan.ctas, 1, 1), GN_THREADS, smem, st>>>(                                        \
+      DICP_CUDA(cudaFuncSetAttribute(gn_accum_staged_kernel<PL, DM, FW, RG, UA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gn_accum_staged_kernel<PL, DM, FW, RG, UA><<<dim3(plan.ctas, 1, 1), GN_THREADS, smem, st>>>(                                    \
         source, target, (pl && rows24) ? nullptr : rows, w_init, idx, state, n, m, P, weights_out, w_pair_stride, partials, plan,  \
         stop_flag, N, n_valid);                                                                                                    \
+  } while (0)
+#define DICP_GN_LAUNCH1(PL, DM, FW, RG)            \
+  do {                                             \
+    if (unal) DICP_GN_LAUNCH2(PL, DM, FW, RG, true); \
+    else DICP_GN_LAUNCH2(PL, DM, FW, RG, false);   \
   } while (0)
 #define DICP_GN_LAUNCH(PL, DM)                                  \
   do {                                                          \
@@ -555,6 +600,7 @@ int gn_accumulate(const T* source, const T* target, const void* rows, const T* w
       else DICP_GN_LAUNCH(false, 2);
 #undef DICP_GN_LAUNCH
 #undef DICP_GN_LAUNCH1
+#undef DICP_GN_LAUNCH2
     }
   } else {
 #define DICP_GN_LAUNCH(PL, DM)                                                                                                     \

@@ -241,11 +241,14 @@ def test_subnormal_distances_are_finite_and_match_oracle():
 
 @pytest.mark.parametrize("icp_type", ["pt2pl", "pt2pt"])
 @pytest.mark.parametrize("N,n", [(1, 4), (3, 8), (1, 12), (2, 252), (1, 256), (3, 260), (2, 508), (5, 512), (1, 516), (2, 1000),
-                                 (7, 1028), (600, 64), (1, 2048), (2, 4100)])
+                                 (7, 1028), (600, 64), (1, 2048), (2, 4100),
+                                 # lengths that are not a multiple of 4: aligned supersets of the slices (UNAL), with N n = 0..3 mod 4
+                                 (1, 5), (3, 9), (2, 255), (3, 257), (1, 1023), (2, 1025), (5, 513), (1, 4099), (3, 4098), (4, 771), (301, 67)])
 def test_tile_ring_edge_shapes_vs_oracle(N, n, icp_type):
     """Shapes around the tile size (256 correspondences), the ring depth (4 stages) and the chunk size of the persistent
-    schedule -- tail tiles, fewer tiles than stages, more pairs than CTAs, one-tile pairs -- through the staged fp32
-    kernels (n % 4 == 0), forward and backward, against the fp64 oracle on the replayed correspondences."""
+    schedule -- tail tiles, fewer tiles than stages, more pairs than CTAs, one-tile pairs, slices that do not start on a
+    16-byte boundary -- through the staged fp32 kernels, forward and backward, against the fp64 oracle on the replayed
+    correspondences."""
     from oracle.dicp_oracle import IcpSettings, icp_forward, make_wavy_pair
     if icp_type == "pt2pl" and n < 64:
         pytest.skip("a handful of point-to-plane rows on a nearly flat surface leave the 6x6 system singular up to the 1e-12 "
