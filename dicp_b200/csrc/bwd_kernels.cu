@@ -226,7 +226,7 @@ __device__ __forceinline__ void scatter_gtab(float* __restrict__ gtab, size_t ro
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fp32 fast path (n % 4 == 0, 16-byte aligned streams, gather table `rows` and gradient table `gtab` present).
+// fp32 fast path (16-byte aligned stream bases, gather table `rows` and gradient table `gtab` present; UNAL when n % 4 != 0).
 // Ring stage = { idx | p | w0 | grad_source | grad_w } slices of the tile; see gn_accum_staged_kernel for the
 // full / empty barrier protocol, the rotating feeder and the state prefetch.
 // ---------------------------------------------------------------------------------------------------------

@@ -138,8 +138,9 @@ __device__ __forceinline__ void gn_enter_segment(GnPairCtx<T>& ctx, int b, long 
 
 // ---------------------------------------------------------------------------------------------------------
 // fp32 fast path: streams staged in shared memory by TMA bulk copies, target rows gathered one tile ahead.
-// Requirements (checked by the launcher): n % 4 == 0 and 16-byte aligned source / idx / w_init, so that every
-// slice of each stream starts on a 16-byte boundary and has a 16-byte multiple length; `rows` built.
+// Requirements (checked by the launcher): 16-byte aligned source / w_init and `rows` built.  With n % 4 == 0 (and an
+// aligned idx) every slice of each stream starts on a 16-byte boundary and has a 16-byte multiple length; otherwise
+// the UNAL instantiation copies the aligned superset of every slice (see st_off / issue).
 //
 // The CTA's ring has STAGES stages of { idx[TILE] | p[3 TILE] | w0[TILE] } with a "full" mbarrier (bulk-copy
 // transaction bytes) and an "empty" mbarrier (one arrival per warp) per stage.  No __syncthreads separates
