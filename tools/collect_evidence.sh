@@ -15,6 +15,11 @@ $NCU -k regex:bwd_points_staged -s 20 -c 1 -o $OUT/${TAG}_full_bwd_112 python to
 $NCU -k regex:bwd_points_staged -s 290 -c 1 -o $OUT/${TAG}_full_bwd_124 python tools/prof_bwd.py > $OUT/${TAG}_full_bwd_124.log 2>&1
 $NCU -k regex:bwd_pair_kernel -s 20 -c 1 -o $OUT/${TAG}_full_bwd_pair python tools/prof_bwd.py > $OUT/${TAG}_full_bwd_pair.log 2>&1
 NO_TORCH_PROFILER=1 $NCU -k regex:gn_update_kernel -s 12 -c 1 -o $OUT/${TAG}_full_gn_update python tools/step_profile.py 256 brute > $OUT/${TAG}_full_gn_update.log 2>&1
+# gpurun brings back at most 64 MiB: summarise the captures here and keep only the two that the source view is read from
+for r in nn_scan gn_accum bwd_112 bwd_124 bwd_pair gn_update; do
+  python tools/ncu_summary.py raw $OUT/${TAG}_full_$r.ncu-rep > $OUT/${TAG}_full_$r.md 2>/dev/null
+done
+rm -f $OUT/${TAG}_full_bwd_112.ncu-rep $OUT/${TAG}_full_bwd_pair.ncu-rep $OUT/${TAG}_full_gn_update.ncu-rep $OUT/${TAG}_full_nn_scan.ncu-rep
 # 3. sanitizers over the tests that drive the kernels changed in this session (staged accumulate / reverse kernels with and
 #    without ragged batches, PDL-chained reverse loop, unrolled solve, sync-free forward, split batches)
 SEL='fixture or dense or ragged or sync_free or more_pairs or n_valid or zero or weight'
